@@ -1,0 +1,125 @@
+// resample_core.cuh -- the pinned resample definition "R-B" (SURVEY 8c): the
+// arithmetic of the reference's own in-tree CUDA scaler, libavfilter/vf_scale_cuda.cu
+// (Subsample_Bicubic :1040-1074, bicubic_coeffs :970-981, lanczos_coeffs :948-968,
+// apply_coeffs :983-992), in the operation order nvcc 12.9 emits for sm_100a (SASS of
+// oracle/_ref/ref_scale_cuda.cubin):
+//
+//   hscale = div.rn((float)src_w, (float)dst_w)
+//   xi = FFMA(xo + 0.5f, hscale, -0.5f);  px = floor(xi);  fx = xi - px
+//   taps at px-1 .. px+2, coordinates clamped to the image (texture clamp mode),
+//   samples p = texel / 255 (u8) or / 65535 (u16), as the texture unit's
+//   normalised-float read returns them
+//   row:  t = FMUL(w1,p1); t = FFMA(w0,p0,t); t = FFMA(w2,p2,t); t = FFMA(w3,p3,t)
+//   the same chain vertically over the 4 row results, then FMUL(t, 255|65535) and
+//   F2I.U32.TRUNC (negative -> 0; values above the maximum are not clamped by the
+//   reference -> they wrap when stored; we saturate unless GMATB_SWS_PARITY_WRAP).
+//
+// The chain is separable exactly as written: the 4 horizontal results of a source
+// row depend only on (row, xo), so computing them once per source row and reusing
+// them for every output row that taps the row performs the reference's operations
+// verbatim -- bit-identical output at a fraction of the work.
+#pragma once
+#include "common.cuh"
+
+namespace gmatb {
+
+enum { RS_BICUBIC = 0, RS_LANCZOS = 1, RS_BILINEAR = 2, RS_NEAREST = 3 };
+
+// bicubic_coeffs (vf_scale_cuda.cu:970-981) in SASS order.  A = 0 when the
+// parameter is the default, else -param.
+__device__ __forceinline__ float4 bicubic_coeffs_rb(float x, float A) {
+    const float x1  = __fadd_rn(x, 1.0f);
+    const float omx = __fadd_rn(-x, 1.0f);
+    const float Ap2 = __fadd_rn(A, 2.0f), Ap3 = __fadd_rn(A, 3.0f);
+    const float A5 = __fmul_rn(A, 5.0f), A4 = __fmul_rn(A, 4.0f);
+    float4 r;
+    float s = __fmaf_rn(x1, A, -A5);            // A*(x+1) - 5A
+    s = __fmul_rn(x1, s);
+    s = __fmaf_rn(A, 8.0f, s);                  // ... + 8A
+    r.x = __fmaf_rn(x1, s, -A4);                // ...*(x+1) - 4A
+    float t = __fmaf_rn(x, Ap2, -Ap3);          // (A+2)x - (A+3)
+    t = __fmul_rn(x, t);
+    r.y = __fmaf_rn(x, t, 1.0f);
+    float u = __fmaf_rn(Ap2, omx, -Ap3);        // (A+2)(1-x) - (A+3)
+    u = __fmul_rn(omx, u);
+    r.z = __fmaf_rn(omx, u, 1.0f);
+    r.w = __fadd_rn(__fadd_rn(__fadd_rn(-r.x, 1.0f), -r.y), -r.z);   // 1 - x - y - z
+    return r;
+}
+
+// lanczos_coeffs (vf_scale_cuda.cu:948-968): a = 2, fast-math sines, normalised.
+__device__ __forceinline__ float lanczos_tap_rb(float t) {
+    if (t == 0.0f) return 1.0f;
+    const float num = __fmul_rn(__sinf(t), __sinf(__fmul_rn(t, 0.5f)));   // t/2.0f == t*0.5f exactly
+    const float den = __fmul_rn(__fmul_rn(t, t), 0.5f);                   // FMUL.D2
+    return __fdiv_rn(num, den);
+}
+__device__ __forceinline__ float4 lanczos_coeffs_rb(float x) {
+    const float pi = 3.141592654f;
+    float4 r;
+    r.x = lanczos_tap_rb(__fmul_rn(pi, __fadd_rn(x, 1.0f)));
+    r.y = lanczos_tap_rb(__fmul_rn(pi, x));
+    r.z = lanczos_tap_rb(__fmul_rn(pi, __fadd_rn(x, -1.0f)));
+    r.w = lanczos_tap_rb(__fmul_rn(pi, __fadd_rn(x, -2.0f)));
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(r.x, r.y), r.z), r.w);
+    r.x = __fdiv_rn(r.x, sum); r.y = __fdiv_rn(r.y, sum); r.z = __fdiv_rn(r.z, sum); r.w = __fdiv_rn(r.w, sum);
+    return r;
+}
+
+// one axis of the filter bank: coeffs[o] (4 taps) and pos[o] = px - 1
+__global__ void filter_table_kernel(int algo, int src_n, int dst_n, float A, float4 *coeffs, int *pos) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= dst_n) return;
+    const float scale = __fdiv_rn((float)src_n, (float)dst_n);
+    float4 c; int p;
+    if (algo == RS_BICUBIC || algo == RS_LANCZOS) {
+        const float xi = __fmaf_rn(__fadd_rn((float)o, 0.5f), scale, -0.5f);
+        const float pf = floorf(xi);
+        const float f = __fadd_rn(xi, -pf);
+        c = algo == RS_BICUBIC ? bicubic_coeffs_rb(f, A) : lanczos_coeffs_rb(f);
+        p = (int)pf - 1;
+    } else if (algo == RS_BILINEAR) {
+        // R-A: half-pixel-centre bilinear, clamp, fp32:
+        // sx = (o+.5)*s - .5; taps at floor(sx), floor(sx)+1 with weights (1-f, f)
+        const float xi = __fmaf_rn(__fadd_rn((float)o, 0.5f), scale, -0.5f);
+        const float pf = floorf(xi);
+        const float f = __fadd_rn(xi, -pf);
+        c = make_float4(0.0f, __fadd_rn(1.0f, -f), f, 0.0f);
+        p = (int)pf - 1;
+    } else {   // nearest: Subsample_Nearest (vf_scale_cuda.cu:998-1007): texel floor((o+.5)*s)
+        const float xi = __fmul_rn(__fadd_rn((float)o, 0.5f), scale);
+        c = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
+        p = (int)floorf(xi) - 1;
+    }
+    coeffs[o] = c;
+    pos[o] = p;
+}
+
+// Quantise-and-normalise one CSC result: r (float, unclamped) -> the sample the
+// reference's resize stage reads back from its u8/u16 intermediate image through the
+// texture unit, p = RN(clamp(trunc(r), 0, max) / max).
+//   m  = FADD.RZ(r, 2^23)           = 2^23 + trunc(r)     (r >= 0; r < 0 gives m < 2^23)
+//   j  = m - 2^23                   exact
+//   p  = sat(FFMA(j, khi, RN(j*klo)))   with khi + klo = 1/max to 48 bits
+// RN(j * RN(1/255)) != RN(j/255) for about half of all j, hence the two-term quotient;
+// it equals the correctly rounded quotient for every j in range (exhaustive check in
+// tests/test_oracle.py), the saturation implements both clamps (j < 0 -> 0, j > max -> 1).
+struct NormK { float khi, klo; };
+
+__device__ __forceinline__ f2 add2_rz(f2 a, f2 b) {
+    f2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+// two values at a time (packed where the ISA allows; .sat exists only on scalar ops)
+__device__ __forceinline__ f2 quant_norm2(f2 r, const NormK &k) {
+    const f2 m = add2_rz(r, bc(GMATB_MAGIC));
+    const f2 j = add2(m, bc(-GMATB_MAGIC));
+    float j0, j1, t0, t1;
+    upk(j, j0, j1);
+    t0 = __fmul_rn(j0, k.klo); t1 = __fmul_rn(j1, k.klo);
+    return pk(fma_sat(j0, k.khi, t0), fma_sat(j1, k.khi, t1));
+}
+
+}  // namespace gmatb

@@ -1,0 +1,490 @@
+// scale.cu -- the scaling context behind SwsContext's CUDA path: what
+// libswscale/cuda/swscale_cuda.c does with CV-CUDA (init :112-271, per-frame :273-479,
+// free :86-110), re-done with our own kernels and no intermediate HBM round trip on the
+// yuv->rgb path.  See include/gmat_b200.h for the C ABI.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "scale_fused.cuh"
+#include "scale_generic.cuh"
+
+namespace gmatb {
+int yuv2rgb_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, cudaStream_t);
+int yuv2rgb_planar_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, float, const float *, cudaStream_t);
+int rgb2yuv_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, cudaStream_t);
+int yuv2yuv_launch(const GmatbImage *, const GmatbImage *, cudaStream_t);
+int rgb24swap_launch(const GmatbImage *, const GmatbImage *, cudaStream_t);
+
+enum { K_YUV2RGB = 0, K_RGB2YUV = 1, K_YUV2YUV = 2, K_RGB2RGB = 3 };
+enum { PATH_UNSCALED = 0, PATH_FUSED2 = 1, PATH_GENERIC = 2 };
+
+static bool is_yuv(int f) {
+    return f == GMATB_FMT_NV12 || f == GMATB_FMT_YUV420P || f == GMATB_FMT_P010LE || f == GMATB_FMT_P016LE ||
+           f == GMATB_FMT_YUV420P10LE || f == GMATB_FMT_YUV420P16LE;
+}
+static bool is_rgb(int f) {
+    switch (f) {
+    case GMATB_FMT_RGB24: case GMATB_FMT_BGR24: case GMATB_FMT_RGBA: case GMATB_FMT_BGRA:
+    case GMATB_FMT_RGB0: case GMATB_FMT_BGR0: case GMATB_FMT_0RGB: case GMATB_FMT_0BGR:
+    case GMATB_FMT_RGB48LE: case GMATB_FMT_BGR48LE: case GMATB_FMT_RGBA64LE: case GMATB_FMT_BGRA64LE:
+    case GMATB_FMT_RGBPF32LE: case GMATB_FMT_RGBAPF32LE: return true;
+    default: return false;
+    }
+}
+static int fmt_bits(int f) {
+    switch (f) {
+    case GMATB_FMT_P010LE: case GMATB_FMT_P016LE: case GMATB_FMT_YUV420P10LE: case GMATB_FMT_YUV420P16LE:
+    case GMATB_FMT_RGB48LE: case GMATB_FMT_BGR48LE: case GMATB_FMT_RGBA64LE: case GMATB_FMT_BGRA64LE: return 16;
+    case GMATB_FMT_RGBPF32LE: case GMATB_FMT_RGBAPF32LE: return 32;
+    default: return 8;
+    }
+}
+static int rgb_channels(int f) {
+    switch (f) {
+    case GMATB_FMT_RGB24: case GMATB_FMT_BGR24: case GMATB_FMT_RGB48LE: case GMATB_FMT_BGR48LE: return 3;
+    default: return 4;
+    }
+}
+static int rgb_dst_code(int fmt) {
+    switch (fmt) {
+    case GMATB_FMT_RGB24: return D_RGB24;   case GMATB_FMT_BGR24: return D_BGR24;
+    case GMATB_FMT_RGBA: case GMATB_FMT_RGB0: return D_RGBA;
+    case GMATB_FMT_BGRA: case GMATB_FMT_BGR0: return D_BGRA;
+    case GMATB_FMT_RGB48LE: return D_RGB48; case GMATB_FMT_BGR48LE: return D_BGR48;
+    case GMATB_FMT_RGBA64LE: return D_RGBA64; case GMATB_FMT_BGRA64LE: return D_BGRA64;
+    default: return -1;
+    }
+}
+}  // namespace gmatb
+
+using namespace gmatb;
+
+struct GmatbSws {
+    int srcW, srcH, srcFmt, dstW, dstH, dstFmt, flags, cspace;
+    double param[2];
+    cudaStream_t stream;
+    int kind, path, algo, ra;
+    float A;
+    Mat9 M;
+    // filter banks: [0] luma/packed axes, [1] chroma axes (yuv->yuv only)
+    float4 *cx[2], *cy[2];
+    int *px[2], *py[2];
+    std::vector<int> hpx[2], hpy[2];
+    float wx[4], wy[4];
+    bool taps2;
+    // scratch
+    void *tmp; size_t tmp_size;
+    void *stage_src, *stage_dst; size_t stage_src_size, stage_dst_size;
+};
+
+static int build_axis(int algo, int srcN, int dstN, float A, float4 **dc, int **dp, std::vector<int> *hp, cudaStream_t st) {
+    if (cudaMalloc(dc, sizeof(float4) * dstN) != cudaSuccess || cudaMalloc(dp, sizeof(int) * dstN) != cudaSuccess)
+        return GMATB_ERR_NOMEM;
+    filter_table_kernel<<<(dstN + 127) / 128, 128, 0, st>>>(algo, srcN, dstN, A, *dc, *dp);
+    count_launch();
+    hp->resize(dstN);
+    cudaError_t e = cudaMemcpyAsync(hp->data(), *dp, sizeof(int) * dstN, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return set_cuda_error(e);
+}
+
+extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat,
+                                      int flags, const double *param, int colorspace) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return nullptr;
+    const bool sy = is_yuv(srcFormat), sr = is_rgb(srcFormat), dy = is_yuv(dstFormat), dr = is_rgb(dstFormat);
+    if (!(sy || sr) || !(dy || dr)) return nullptr;
+    GmatbSws *c = new GmatbSws();
+    memset(c, 0, offsetof(GmatbSws, hpx));
+    c->tmp = c->stage_src = c->stage_dst = nullptr;
+    c->tmp_size = c->stage_src_size = c->stage_dst_size = 0;
+    c->srcW = srcW; c->srcH = srcH; c->srcFmt = srcFormat; c->dstW = dstW; c->dstH = dstH; c->dstFmt = dstFormat;
+    c->flags = flags; c->cspace = colorspace; c->stream = 0;
+    c->param[0] = param ? param[0] : GMATB_SWS_PARAM_DEFAULT;
+    c->param[1] = param ? param[1] : GMATB_SWS_PARAM_DEFAULT;
+    c->kind = sy ? (dr ? K_YUV2RGB : K_YUV2YUV) : (dy ? K_RGB2YUV : K_RGB2RGB);
+    if (c->kind == K_RGB2YUV) gmatb_csc_matrix_rgb2yuv(colorspace, c->M.m);
+    else gmatb_csc_matrix_yuv2rgb(colorspace, c->M.m);
+
+    if (srcW == dstW && srcH == dstH) {   // sws_init_context_cuda: unscaled (utils.c:2048-2055)
+        c->path = PATH_UNSCALED;
+        if (c->kind == K_RGB2RGB && srcFormat != dstFormat &&
+            !((srcFormat == GMATB_FMT_RGB24 && dstFormat == GMATB_FMT_BGR24) ||
+              (srcFormat == GMATB_FMT_BGR24 && dstFormat == GMATB_FMT_RGB24))) { delete c; return nullptr; }
+        return c;
+    }
+    // ---- scaled --------------------------------------------------------------------
+    if (fmt_bits(srcFormat) == 32 || fmt_bits(dstFormat) == 32) { delete c; return nullptr; }
+    if (c->kind == K_YUV2RGB && (rgb_dst_code(dstFormat) < 0 || fmt_bits(srcFormat) != fmt_bits(dstFormat))) { delete c; return nullptr; }
+    if (c->kind == K_RGB2RGB && srcFormat != dstFormat) { delete c; return nullptr; }
+    if (c->kind == K_RGB2YUV && (fmt_bits(srcFormat) != 8 || fmt_bits(dstFormat) != 8)) { delete c; return nullptr; }
+    if (c->kind == K_YUV2YUV && ((srcW | srcH | dstW | dstH) & 1)) { delete c; return nullptr; }
+
+    // algorithm from the SWS_* bit (the reference intends this mapping, swscale_cuda.c:69-74;
+    // its own call site passes the wrong field, :305, and always gets LINEAR)
+    if (flags & GMATB_SWS_BICUBIC) c->algo = RS_BICUBIC;
+    else if (flags & GMATB_SWS_LANCZOS) c->algo = RS_LANCZOS;
+    else if (flags & GMATB_SWS_POINT) c->algo = RS_NEAREST;
+    else c->algo = RS_BILINEAR;   // SWS_BILINEAR, SWS_FAST_BILINEAR, SWS_AREA, nothing: map_resize_algo's fallthrough
+    c->ra = (c->algo == RS_BILINEAR || c->algo == RS_NEAREST);
+    const bool pdef = (c->param[0] == GMATB_SWS_PARAM_DEFAULT);
+    c->A = pdef ? 0.0f : -(float)c->param[0];   // vf_scale_cuda.cu:972
+
+    int rc = build_axis(c->algo, srcW, dstW, c->A, &c->cx[0], &c->px[0], &c->hpx[0], 0);
+    if (!rc) rc = build_axis(c->algo, srcH, dstH, c->A, &c->cy[0], &c->py[0], &c->hpy[0], 0);
+    if (!rc && c->kind == K_YUV2YUV) {
+        rc = build_axis(c->algo, srcW / 2, dstW / 2, c->A, &c->cx[1], &c->px[1], &c->hpx[1], 0);
+        if (!rc) rc = build_axis(c->algo, srcH / 2, dstH / 2, c->A, &c->cy[1], &c->py[1], &c->hpy[1], 0);
+    }
+    if (rc) { gmatb_sws_free(c); return nullptr; }
+
+    c->path = PATH_GENERIC;
+    const bool sparse = c->M.m[1] == 0.f && c->M.m[8] == 0.f;
+    if (c->kind == K_YUV2RGB && !c->ra && sparse && srcW == 2 * dstW && srcH == 2 * dstH && (srcW % 8) == 0) {
+        float4 hx, hy;
+        cudaMemcpy(&hx, c->cx[0], sizeof(hx), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&hy, c->cy[0], sizeof(hy), cudaMemcpyDeviceToHost);
+        c->wx[0] = hx.x; c->wx[1] = hx.y; c->wx[2] = hx.z; c->wx[3] = hx.w;
+        c->wy[0] = hy.x; c->wy[1] = hy.y; c->wy[2] = hy.z; c->wy[3] = hy.w;
+        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
+        c->path = PATH_FUSED2;
+    }
+    return c;
+}
+
+extern "C" void gmatb_sws_free(GmatbSws *c) {
+    if (!c) return;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->cx[i]); cudaFree(c->cy[i]); cudaFree(c->px[i]); cudaFree(c->py[i]);
+    }
+    cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst);
+    delete c;
+}
+extern "C" void gmatb_sws_set_stream(GmatbSws *c, void *stream) { if (c) c->stream = (cudaStream_t)stream; }
+extern "C" int gmatb_sws_path(const GmatbSws *c) { return c ? c->path : GMATB_ERR_INVAL; }
+
+extern "C" int gmatb_sws_get_filter(GmatbSws *c, int axis, float *coeffs, int *pos) {
+    if (!c || c->path == PATH_UNSCALED || axis < 0 || axis > 1) return GMATB_ERR_INVAL;
+    const int n = axis == 0 ? c->dstW : c->dstH;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && coeffs) e = cudaMemcpy(coeffs, axis == 0 ? c->cx[0] : c->cy[0], sizeof(float4) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && pos) e = cudaMemcpy(pos, axis == 0 ? c->px[0] : c->py[0], sizeof(int) * n, cudaMemcpyDeviceToHost);
+    return set_cuda_error(e);
+}
+
+// ------------------------------------------------------------------------------------
+namespace gmatb {
+
+static NormK norm_k(int bits) {
+    const double inv = 1.0 / (bits == 8 ? 255.0 : 65535.0);
+    NormK k;
+    k.khi = (float)inv;
+    k.klo = (float)(inv - (double)k.khi);
+    return k;
+}
+
+template <int L, int SBITS, int DST>
+static void launch_fused_t(bool taps2, dim3 g, cudaStream_t st, const Fused2Params &P) {
+    if (taps2) fused_csc_scale2_kernel<L, SBITS, DST, true, true><<<g, 32, 0, st>>>(P);
+    else       fused_csc_scale2_kernel<L, SBITS, DST, true, false><<<g, 32, 0, st>>>(P);
+}
+template <int L, int SBITS>
+static int launch_fused_d(int dc, bool taps2, dim3 g, cudaStream_t st, const Fused2Params &P) {
+    if (SBITS == 8) {
+        switch (dc) {
+        case D_RGB24: launch_fused_t<L, SBITS, D_RGB24>(taps2, g, st, P); break;
+        case D_BGR24: launch_fused_t<L, SBITS, D_BGR24>(taps2, g, st, P); break;
+        case D_RGBA:  launch_fused_t<L, SBITS, D_RGBA>(taps2, g, st, P); break;
+        case D_BGRA:  launch_fused_t<L, SBITS, D_BGRA>(taps2, g, st, P); break;
+        default: return GMATB_ERR_UNSUPPORTED;
+        }
+    } else {
+        switch (dc) {
+        case D_RGB48:  launch_fused_t<L, SBITS, D_RGB48>(taps2, g, st, P); break;
+        case D_BGR48:  launch_fused_t<L, SBITS, D_BGR48>(taps2, g, st, P); break;
+        case D_RGBA64: launch_fused_t<L, SBITS, D_RGBA64>(taps2, g, st, P); break;
+        case D_BGRA64: launch_fused_t<L, SBITS, D_BGRA64>(taps2, g, st, P); break;
+        default: return GMATB_ERR_UNSUPPORTED;
+        }
+    }
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+static bool planes_aligned(const Img &a, int np, int al) {
+    for (int i = 0; i < np; i++)
+        if (((uintptr_t)a.pl[i].p | (uintptr_t)a.pl[i].pitch | (uintptr_t)a.pl[i].bstride) & (al - 1)) return false;
+    return true;
+}
+
+static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
+    *done = false;
+    Fused2Params P;
+    const int np = fmt_planes(src->format);
+    if (!to_img(src, &P.src, np) || !to_img(dst, &P.dst, 1)) return GMATB_ERR_INVAL;
+    const int bits = fmt_bits(src->format);
+    const int dc = rgb_dst_code(dst->format);
+    const bool semi = np == 2;
+    // vector-access preconditions; otherwise the generic kernel takes the frame
+    if (!planes_aligned(P.src, 1, bits == 8 ? 8 : 16)) return 0;
+    if (semi ? !planes_aligned(P.src, 2, bits == 8 ? 8 : 16) : !(planes_aligned(P.src, 3, bits == 8 ? 4 : 8))) return 0;
+    const int dal = (dc == D_RGB24 || dc == D_BGR24) ? 4 : (dc == D_RGB48 || dc == D_BGR48) ? 8 : 16;
+    if (!planes_aligned(P.dst, 1, dal)) return 0;
+    P.M = c->M;
+    for (int i = 0; i < 4; i++) { P.wx[i] = c->wx[i]; P.wy[i] = c->wy[i]; }
+    P.nk = norm_k(bits);
+    P.factor = bits == 8 ? 255.f : 65535.f;
+    P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
+    P.dstW = c->dstW; P.dstH = c->dstH;
+    const int batch = src->batch > 1 ? src->batch : 1;
+    const int warps_x = (c->srcW / 8 + 31) / 32;
+    // enough warps to fill 148 SMs x 16 resident warps a few times over, but bands no
+    // shorter than 8 output rows (each band re-converts 2 extra chroma rows)
+    long long want = 148LL * 16 * 4;
+    int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
+    nb = std::max(1, std::min(nb, (c->dstH + 7) / 8));
+    P.band = (c->dstH + nb - 1) / nb;
+    nb = (c->dstH + P.band - 1) / P.band;
+    dim3 g(warps_x, nb, batch);
+    int rc;
+    if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, g, c->stream, P);
+    else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, g, c->stream, P);
+    *done = (rc == 0);
+    return rc;
+}
+
+// generic kernel on one "image" (a yuv frame -> rgb, or one packed plane -> same layout)
+static int run_generic(GmatbSws *c, int bank, const Img &s, const Img &d, int dW, int dH, int src_kind, int ch,
+                       int bits, int dst_code, int batch) {
+    GenParams P;
+    P.src = s; P.dst = d; P.M = c->M; P.nk = norm_k(bits);
+    P.factor = bits == 8 ? 255.f : 65535.f; P.vmax = P.factor;
+    P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
+    P.cx = c->cx[bank]; P.cy = c->cy[bank]; P.px = c->px[bank]; P.py = c->py[bank];
+    P.dstW = dW; P.dstH = dH; P.src_kind = src_kind; P.ch = ch; P.dst_code = dst_code; P.sparse = 0;
+    const std::vector<int> &hx = c->hpx[bank], &hy = c->hpy[bank];
+    int tw = 32, th = 8;
+    size_t smem = 0;
+    for (;;) {   // shrink the tile until the window fits in shared memory
+        int mw = 0, mh = 0;
+        for (int x = 0; x < dW; x += tw) mw = std::max(mw, hx[std::min(x + tw, dW) - 1] + 4 - hx[x]);
+        for (int y = 0; y < dH; y += th) mh = std::max(mh, hy[std::min(y + th, dH) - 1] + 4 - hy[y]);
+        smem = ((size_t)mw * mh + (size_t)mh * tw) * ch * sizeof(float);
+        P.win_w = mw; P.win_h = mh;
+        if (smem <= 160 * 1024 || (tw == 1 && th == 1)) break;
+        if (tw >= th && tw > 1) tw /= 2; else if (th > 1) th /= 2; else tw /= 2;
+    }
+    if (smem > 200 * 1024) return GMATB_ERR_UNSUPPORTED;
+    P.tile_w = tw; P.tile_h = th;
+    dim3 g((dW + tw - 1) / tw, (dH + th - 1) / th, batch > 1 ? batch : 1);
+    cudaError_t e = cudaSuccess;
+#define GO(B, R) do { \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(generic_scale_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) generic_scale_kernel<B, R><<<g, 256, smem, c->stream>>>(P); } while (0)
+    if (bits == 8) { if (c->ra) GO(8, 1); else GO(8, 0); }
+    else           { if (c->ra) GO(16, 1); else GO(16, 0); }
+#undef GO
+    if (e != cudaSuccess) return set_cuda_error(e);
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+static int ensure(void **p, size_t *have, size_t need) {
+    if (*have >= need) return 0;
+    cudaFree(*p); *p = nullptr; *have = 0;
+    if (cudaMalloc(p, need) != cudaSuccess) return GMATB_ERR_NOMEM;
+    *have = need;
+    return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// describe a tightly laid out (pitch aligned to 256) image of `fmt` in a scratch buffer
+static size_t layout_image(GmatbImage *g, int fmt, int w, int h, int batch, uint8_t *base) {
+    memset(g, 0, sizeof(*g));
+    g->format = fmt; g->width = w; g->height = h; g->batch = batch;
+    size_t off = 0, frame = 0;
+    const int bytes = fmt_bits(fmt) / 8;
+    int np = fmt_planes(fmt);
+    size_t psize[4] = {0, 0, 0, 0};
+    if (is_yuv(fmt)) {
+        g->linesize[0] = (int)align_up((size_t)w * bytes, 256);
+        psize[0] = (size_t)g->linesize[0] * h;
+        const int cw = (w + 1) / 2, chh = (h + 1) / 2;
+        if (np == 2) { g->linesize[1] = (int)align_up((size_t)cw * 2 * bytes, 256); psize[1] = (size_t)g->linesize[1] * chh; }
+        else { g->linesize[1] = g->linesize[2] = (int)align_up((size_t)cw * bytes, 256); psize[1] = psize[2] = (size_t)g->linesize[1] * chh; }
+    } else {
+        np = 1;
+        g->linesize[0] = (int)align_up((size_t)w * rgb_channels(fmt) * bytes, 256);
+        psize[0] = (size_t)g->linesize[0] * h;
+    }
+    for (int i = 0; i < np; i++) frame += psize[i];
+    for (int i = 0; i < np; i++) { g->data[i] = base ? base + off : nullptr; g->batch_stride[i] = (long long)frame; off += psize[i]; }
+    return frame * (batch > 1 ? batch : 1);
+}
+
+static void fix_nv12_uv(GmatbImage *g) {
+    // the reference's NV12/P016 kernels take one pointer and find UV at src + H*pitch
+    // (yuv2rgb_cuda.cu:226); accept callers that pass only data[0]
+    if ((g->format == GMATB_FMT_NV12 || g->format == GMATB_FMT_P010LE || g->format == GMATB_FMT_P016LE) && !g->data[1] && g->data[0]) {
+        g->data[1] = (uint8_t *)g->data[0] + (size_t)g->height * g->linesize[0];
+        g->linesize[1] = g->linesize[0];
+        g->batch_stride[1] = g->batch_stride[0];
+    }
+}
+
+static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const GmatbImage *d, int plane, int pw, int ph,
+                          int dw, int dh, int ch, int bits) {
+    Img si, di;
+    memset(&si, 0, sizeof(si)); memset(&di, 0, sizeof(di));
+    si.w = pw; si.h = ph; di.w = dw; di.h = dh;
+    si.pl[0].p = (uint8_t *)s->data[plane]; si.pl[0].pitch = s->linesize[plane]; si.pl[0].bstride = s->batch > 1 ? s->batch_stride[plane] : 0;
+    di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
+    if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
+    return run_generic(c, bank, si, di, dw, dh, GS_PACKED, ch, bits, 0, s->batch);
+}
+
+static int scale_batch(GmatbSws *c, const GmatbImage *src_in, const GmatbImage *dst_in) {
+    if (!c || !src_in || !dst_in) return GMATB_ERR_INVAL;
+    GmatbImage src = *src_in, dst = *dst_in;
+    if (src.width != c->srcW || src.height != c->srcH || dst.width != c->dstW || dst.height != c->dstH ||
+        src.format != c->srcFmt || dst.format != c->dstFmt) return GMATB_ERR_INVAL;
+    if ((src.batch > 1 ? src.batch : 1) != (dst.batch > 1 ? dst.batch : 1)) return GMATB_ERR_INVAL;
+    fix_nv12_uv(&src); fix_nv12_uv(&dst);
+    const int batch = src.batch > 1 ? src.batch : 1;
+
+    if (c->path == PATH_UNSCALED) {
+        switch (c->kind) {
+        case K_YUV2RGB:
+            if (fmt_bits(dst.format) == 32) {
+                if (dst.format == GMATB_FMT_RGBPF32LE && !dst.data[1]) {   // single pointer, planes stacked (yuv2rgb_cuda.cu:420-422)
+                    for (int p = 1; p < 3; p++) {
+                        dst.data[p] = (uint8_t *)dst.data[0] + (size_t)p * dst.height * dst.linesize[0];
+                        dst.linesize[p] = dst.linesize[0]; dst.batch_stride[p] = dst.batch_stride[0];
+                    }
+                }
+                return yuv2rgb_planar_launch(&src, &dst, c->M, 255.0f, nullptr, c->stream);
+            }
+            return yuv2rgb_launch(&src, &dst, c->M, c->stream);
+        case K_RGB2YUV: return rgb2yuv_launch(&src, &dst, c->M, c->stream);
+        case K_YUV2YUV: return yuv2yuv_launch(&src, &dst, c->stream);
+        default:
+            if (src.format != dst.format) return rgb24swap_launch(&src, &dst, c->stream);
+            {
+                const size_t row = (size_t)src.width * rgb_channels(src.format) * (fmt_bits(src.format) / 8);
+                for (int i = 0; i < batch; i++) {
+                    cudaError_t e = cudaMemcpy2DAsync((uint8_t *)dst.data[0] + i * dst.batch_stride[0], dst.linesize[0],
+                                                      (const uint8_t *)src.data[0] + i * src.batch_stride[0], src.linesize[0],
+                                                      row, src.height, cudaMemcpyDeviceToDevice, c->stream);
+                    if (e != cudaSuccess) return set_cuda_error(e);
+                }
+                return 0;
+            }
+        }
+    }
+
+    const int bits = fmt_bits(src.format);
+    if (c->kind == K_YUV2RGB) {
+        if (c->path == PATH_FUSED2) {
+            bool done = false;
+            int rc = run_fused(c, &src, &dst, &done);
+            if (rc || done) return rc;
+        }
+        Img s, d;
+        const int np = fmt_planes(src.format);
+        if (!to_img(&src, &s, np) || !to_img(&dst, &d, 1)) return GMATB_ERR_INVAL;
+        return run_generic(c, 0, s, d, c->dstW, c->dstH, np == 2 ? GS_NV12 : GS_I420, 3, bits, rgb_dst_code(dst.format), batch);
+    }
+    if (c->kind == K_RGB2RGB) {
+        return plane_resample(c, 0, &src, &dst, 0, c->srcW, c->srcH, c->dstW, c->dstH, rgb_channels(src.format), bits);
+    }
+    if (c->kind == K_RGB2YUV) {   // resize first, convert at destination size (swscale_cuda.c:312-341)
+        GmatbImage tmp;
+        size_t need = layout_image(&tmp, src.format, c->dstW, c->dstH, batch, nullptr);
+        if (ensure(&c->tmp, &c->tmp_size, need)) return GMATB_ERR_NOMEM;
+        layout_image(&tmp, src.format, c->dstW, c->dstH, batch, (uint8_t *)c->tmp);
+        int rc = plane_resample(c, 0, &src, &tmp, 0, c->srcW, c->srcH, c->dstW, c->dstH, rgb_channels(src.format), bits);
+        if (rc) return rc;
+        return rgb2yuv_launch(&tmp, &dst, c->M, c->stream);
+    }
+    // K_YUV2YUV: repack to the destination format at source size, then scale each plane
+    // (swscale_cuda.c:372-476)
+    GmatbImage cur = src;
+    if (src.format != dst.format) {
+        GmatbImage tmp;
+        size_t need = layout_image(&tmp, dst.format, c->srcW, c->srcH, batch, nullptr);
+        if (ensure(&c->tmp, &c->tmp_size, need)) return GMATB_ERR_NOMEM;
+        layout_image(&tmp, dst.format, c->srcW, c->srcH, batch, (uint8_t *)c->tmp);
+        int rc = yuv2yuv_launch(&src, &tmp, c->stream);
+        if (rc) return rc;
+        cur = tmp;
+    }
+    const int dbits = fmt_bits(dst.format);
+    int rc = plane_resample(c, 0, &cur, &dst, 0, c->srcW, c->srcH, c->dstW, c->dstH, 1, dbits);
+    if (rc) return rc;
+    if (fmt_planes(dst.format) == 2)
+        return plane_resample(c, 1, &cur, &dst, 1, c->srcW / 2, c->srcH / 2, c->dstW / 2, c->dstH / 2, 2, dbits);
+    rc = plane_resample(c, 1, &cur, &dst, 1, c->srcW / 2, c->srcH / 2, c->dstW / 2, c->dstH / 2, 1, dbits);
+    if (rc) return rc;
+    return plane_resample(c, 1, &cur, &dst, 2, c->srcW / 2, c->srcH / 2, c->dstW / 2, c->dstH / 2, 1, dbits);
+}
+
+// byte span [lo, hi) covered by an image's planes (all frames)
+static void image_span(const GmatbImage *g, uintptr_t *lo, uintptr_t *hi) {
+    *lo = ~(uintptr_t)0; *hi = 0;
+    const int batch = g->batch > 1 ? g->batch : 1;
+    const int np = is_yuv(g->format) ? fmt_planes(g->format) : (fmt_bits(g->format) == 32 ? fmt_planes(g->format) : 1);
+    for (int p = 0; p < np; p++) {
+        if (!g->data[p]) continue;
+        int rows = g->height;
+        if (is_yuv(g->format) && p > 0) rows = (g->height + 1) / 2;
+        uintptr_t a = (uintptr_t)g->data[p];
+        uintptr_t b = a + (size_t)(batch - 1) * g->batch_stride[p] + (size_t)rows * g->linesize[p];
+        *lo = std::min(*lo, a); *hi = std::max(*hi, b);
+    }
+}
+
+}  // namespace gmatb
+
+extern "C" int gmatb_sws_scale_batch(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst) {
+    return scale_batch(c, src, dst);
+}
+
+extern "C" int gmatb_sws_scale(GmatbSws *c, const uint8_t *const src[4], const int srcStride[4],
+                               uint8_t *const dst[4], const int dstStride[4]) {
+    if (!c || !src || !dst || !srcStride || !dstStride) return GMATB_ERR_INVAL;
+    GmatbImage s, d;
+    memset(&s, 0, sizeof(s)); memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 4; i++) { s.data[i] = (void *)src[i]; s.linesize[i] = srcStride[i]; d.data[i] = dst[i]; d.linesize[i] = dstStride[i]; }
+    s.width = c->srcW; s.height = c->srcH; s.format = c->srcFmt; s.batch = 1;
+    d.width = c->dstW; d.height = c->dstH; d.format = c->dstFmt; d.batch = 1;
+    return scale_batch(c, &s, &d);
+}
+
+// HOST frames in, HOST frames out.  The device staging buffers mirror the host layout
+// byte for byte (same strides), so each direction is ONE async copy of the span.
+extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, const GmatbImage *dst_host) {
+    if (!c || !src_host || !dst_host) return GMATB_ERR_INVAL;
+    GmatbImage s = *src_host, d = *dst_host;
+    fix_nv12_uv(&s); fix_nv12_uv(&d);
+    uintptr_t slo, shi, dlo, dhi;
+    image_span(&s, &slo, &shi); image_span(&d, &dlo, &dhi);
+    if (shi <= slo || dhi <= dlo) return GMATB_ERR_INVAL;
+    // keep the low address bits so that alignment-dependent fast paths still apply
+    const size_t spad = slo & 255, dpad = dlo & 255;
+    if (ensure(&c->stage_src, &c->stage_src_size, (shi - slo) + 256) || ensure(&c->stage_dst, &c->stage_dst_size, (dhi - dlo) + 256))
+        return GMATB_ERR_NOMEM;
+    uint8_t *ds = (uint8_t *)c->stage_src + spad, *dd = (uint8_t *)c->stage_dst + dpad;
+    GmatbImage sdev = s, ddev = d;
+    for (int p = 0; p < 4; p++) {
+        if (s.data[p]) sdev.data[p] = ds + ((uintptr_t)s.data[p] - slo);
+        if (d.data[p]) ddev.data[p] = dd + ((uintptr_t)d.data[p] - dlo);
+    }
+    cudaError_t e = cudaMemcpyAsync(ds, (const void *)slo, shi - slo, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    int rc = scale_batch(c, &sdev, &ddev);
+    if (rc) return rc;
+    e = cudaMemcpyAsync((void *)dlo, dd, dhi - dlo, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return set_cuda_error(e);
+}

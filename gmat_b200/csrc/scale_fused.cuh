@@ -1,0 +1,282 @@
+// scale_fused.cuh -- the headline kernel: YUV 4:2:0 -> packed RGB colour conversion
+// FUSED with an exact 2:1 four-tap resample (4K NV12 -> 1080p RGB24, 8K P010 -> 4K RGB48).
+//
+// The reference runs two kernels with a full-resolution RGB image written to and read
+// back from HBM in between (swscale_cuda.c:342-371: yuv2rgb_cuda -> cvcudaResizeSubmit;
+// 68.4 MB of traffic per 4K frame).  Here the source is read once and only the
+// destination is written (18.7 MB): 2.25 bytes per source pixel.
+//
+// Work decomposition -- "register-streaming column strips":
+//   * a thread owns a strip of 8 source columns (= 4 output columns) and walks down the
+//     frame one chroma row (= 2 luma rows) per iteration; a warp therefore reads 256
+//     contiguous luma bytes per row (64-bit coalesced loads), loads for the next
+//     iteration are issued before the current one is consumed;
+//   * per iteration the 8x2 pixels are converted with the reference's CSC chain packed
+//     as (top,bottom) f32x2 pairs (the two rows share their chroma), quantised to the
+//     u8/u16 value the reference's intermediate image would hold and normalised the way
+//     its texture fetch does;
+//   * the horizontal 4-tap pass runs packed over the row pair; the two halo columns come
+//     from the neighbouring lanes by warp shuffle (lanes 0 and 31 convert their one
+//     missing column themselves);
+//   * the vertical pass is a running accumulation in the reference's operand order
+//     (row 2yo first, then 2yo-1, 2yo+1, 2yo+2): only 12 partial sums + 12 saved
+//     horizontal results are carried between iterations, no shared memory, no barriers;
+//   * output rows leave as 12/16/24/32-byte pieces per thread, contiguous across the warp.
+// The frame is cut into horizontal bands (blockIdx.y) and frames of a batch sit on
+// blockIdx.z, so one launch covers a whole batch with tens of thousands of warps.
+#pragma once
+#include "csc_core.cuh"
+#include "resample_core.cuh"
+
+namespace gmatb {
+
+struct Fused2Params {
+    Img src, dst;
+    Mat9 M;
+    float wx[4], wy[4];
+    NormK nk;
+    float factor;      // 255 or 65535
+    int band;          // output rows per band
+    int wrap;          // GMATB_SWS_PARITY_WRAP
+    int dstW, dstH;
+};
+
+template <int SBITS> struct RawRow;   // raw loaded words of one row pair
+template <> struct RawRow<8>  { uint2 yt, yb, c0; };   // I420: c0.x = 4 U bytes, c0.y = 4 V bytes
+template <> struct RawRow<16> { uint4 yt, yb, c0; };   // I420: c0.xy = 4 U, c0.zw = 4 V
+
+template <int L>
+__device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRow<8> &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const int rc = min(max(k, 0), (H >> 1) - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+    R.yt = ldg64(py + (size_t)rt * P.src.pl[0].pitch + xs);
+    R.yb = ldg64(py + (size_t)rb * P.src.pl[0].pitch + xs);
+    if (L == L_NV12) {
+        R.c0 = ldg64(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs);
+    } else {
+        R.c0.x = ldg32(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xs >> 1));
+        R.c0.y = ldg32(P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + (xs >> 1));
+    }
+}
+template <int L>
+__device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRow<16> &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const int rc = min(max(k, 0), (H >> 1) - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+    R.yt = ldg128(py + (size_t)rt * P.src.pl[0].pitch + xs * 2);
+    R.yb = ldg128(py + (size_t)rb * P.src.pl[0].pitch + xs * 2);
+    if (L == L_NV12) {
+        R.c0 = ldg128(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs * 2);
+    } else {
+        uint2 u = ldg64(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs);
+        uint2 v = ldg64(P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + xs);
+        R.c0 = make_uint4(u.x, u.y, v.x, v.y);
+    }
+}
+
+// unpack the raw words into magic floats: ym[row][col], um/vm[chroma sample]
+template <int L>
+__device__ __forceinline__ void fused_unpack(const RawRow<8> &R, float (&yt)[8], float (&yb)[8], float (&um)[4], float (&vm)[4]) {
+    yt[0] = byte_magic<0>(R.yt.x); yt[1] = byte_magic<1>(R.yt.x); yt[2] = byte_magic<2>(R.yt.x); yt[3] = byte_magic<3>(R.yt.x);
+    yt[4] = byte_magic<0>(R.yt.y); yt[5] = byte_magic<1>(R.yt.y); yt[6] = byte_magic<2>(R.yt.y); yt[7] = byte_magic<3>(R.yt.y);
+    yb[0] = byte_magic<0>(R.yb.x); yb[1] = byte_magic<1>(R.yb.x); yb[2] = byte_magic<2>(R.yb.x); yb[3] = byte_magic<3>(R.yb.x);
+    yb[4] = byte_magic<0>(R.yb.y); yb[5] = byte_magic<1>(R.yb.y); yb[6] = byte_magic<2>(R.yb.y); yb[7] = byte_magic<3>(R.yb.y);
+    if (L == L_NV12) {
+        um[0] = byte_magic<0>(R.c0.x); vm[0] = byte_magic<1>(R.c0.x); um[1] = byte_magic<2>(R.c0.x); vm[1] = byte_magic<3>(R.c0.x);
+        um[2] = byte_magic<0>(R.c0.y); vm[2] = byte_magic<1>(R.c0.y); um[3] = byte_magic<2>(R.c0.y); vm[3] = byte_magic<3>(R.c0.y);
+    } else {
+        um[0] = byte_magic<0>(R.c0.x); um[1] = byte_magic<1>(R.c0.x); um[2] = byte_magic<2>(R.c0.x); um[3] = byte_magic<3>(R.c0.x);
+        vm[0] = byte_magic<0>(R.c0.y); vm[1] = byte_magic<1>(R.c0.y); vm[2] = byte_magic<2>(R.c0.y); vm[3] = byte_magic<3>(R.c0.y);
+    }
+}
+template <int L>
+__device__ __forceinline__ void fused_unpack(const RawRow<16> &R, float (&yt)[8], float (&yb)[8], float (&um)[4], float (&vm)[4]) {
+    yt[0] = half_magic<0>(R.yt.x); yt[1] = half_magic<1>(R.yt.x); yt[2] = half_magic<0>(R.yt.y); yt[3] = half_magic<1>(R.yt.y);
+    yt[4] = half_magic<0>(R.yt.z); yt[5] = half_magic<1>(R.yt.z); yt[6] = half_magic<0>(R.yt.w); yt[7] = half_magic<1>(R.yt.w);
+    yb[0] = half_magic<0>(R.yb.x); yb[1] = half_magic<1>(R.yb.x); yb[2] = half_magic<0>(R.yb.y); yb[3] = half_magic<1>(R.yb.y);
+    yb[4] = half_magic<0>(R.yb.z); yb[5] = half_magic<1>(R.yb.z); yb[6] = half_magic<0>(R.yb.w); yb[7] = half_magic<1>(R.yb.w);
+    if (L == L_NV12) {
+        um[0] = half_magic<0>(R.c0.x); vm[0] = half_magic<1>(R.c0.x); um[1] = half_magic<0>(R.c0.y); vm[1] = half_magic<1>(R.c0.y);
+        um[2] = half_magic<0>(R.c0.z); vm[2] = half_magic<1>(R.c0.z); um[3] = half_magic<0>(R.c0.w); vm[3] = half_magic<1>(R.c0.w);
+    } else {
+        um[0] = half_magic<0>(R.c0.x); um[1] = half_magic<1>(R.c0.x); um[2] = half_magic<0>(R.c0.y); um[3] = half_magic<1>(R.c0.y);
+        vm[0] = half_magic<0>(R.c0.z); vm[1] = half_magic<1>(R.c0.z); vm[2] = half_magic<0>(R.c0.w); vm[3] = half_magic<1>(R.c0.w);
+    }
+}
+
+// one source column (top,bottom) -> normalised (r,g,b) pairs
+template <int SBITS, bool SPARSE>
+__device__ __forceinline__ void fused_column(float ytm, float ybm, const ChromaTerms &t, const Fused2Params &P, f2 (&out)[3]) {
+    constexpr float YB = -(GMATB_MAGIC + (SBITS == 8 ? 16.f : 4096.f));
+    f2 r, g, b;
+    csc_pair_f<SPARSE>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
+    out[0] = quant_norm2(r, P.nk); out[1] = quant_norm2(g, P.nk); out[2] = quant_norm2(b, P.nk);
+}
+
+__device__ __forceinline__ f2 shfl_up2(f2 v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ f2 shfl_dn2(f2 v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <bool TAPS2>
+__device__ __forceinline__ f2 hpass(const float (&w)[4], f2 p0, f2 p1, f2 p2, f2 p3) {
+    f2 t = mul2(bc(w[1]), p1);
+    if (!TAPS2) t = fma2(bc(w[0]), p0, t);
+    t = fma2(bc(w[2]), p2, t);
+    if (!TAPS2) t = fma2(bc(w[3]), p3, t);
+    return t;
+}
+
+// DST: D_* code from csc.cu (packed rgb).  TAPS2: the outer weights of both axes are
+// exactly zero (default bicubic, A = 0, at 2:1), FFMA(0, p, t) == t is skipped.
+template <int L, int SBITS, int DST, bool SPARSE, bool TAPS2>
+__global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params P) {
+    const int lane = threadIdx.x;
+    const int W = P.src.w;
+    const int x0 = (blockIdx.x * 32 + lane) * 8;
+    const bool active = x0 < W;
+    const int xs = active ? x0 : W - 8;
+    const long long fz = blockIdx.z;
+    const int yo_begin = blockIdx.y * P.band;
+    const int yo_end = min(yo_begin + P.band, P.dstH);
+    const bool ledge = xs == 0, redge = xs + 8 == W;
+    const bool need_extra = (lane == 0 && !ledge) || (lane == 31 && !redge);
+    const int xe = lane == 0 ? max(xs - 1, 0) : min(xs + 8, W - 1);
+    constexpr int SB = SBITS / 8;
+    constexpr float CB = -(GMATB_MAGIC + (SBITS == 8 ? 128.f : 32768.f));
+
+    float hb_prev[4][3];   // horizontal results of the previous pair's bottom row
+    float acc[4][3];       // partial vertical sums of the output row in flight
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { hb_prev[i][c] = 0.f; acc[i][c] = 0.f; }
+
+    // constant alpha of 4-channel outputs: the chain applied to a constant 1.0 image
+    int alpha_i = 0;
+    if (dst_alpha(DST)) {
+        // the reference's intermediate alpha is 255 in either depth (yuv2rgb_cuda.cu:89)
+        const float one = SBITS == 8 ? 1.0f : 255.0f / 65535.0f;
+        float ah = __fmul_rn(P.wx[1], one);
+        ah = __fmaf_rn(P.wx[0], one, ah); ah = __fmaf_rn(P.wx[2], one, ah); ah = __fmaf_rn(P.wx[3], one, ah);
+        float av = __fmul_rn(P.wy[1], ah);
+        av = __fmaf_rn(P.wy[0], ah, av); av = __fmaf_rn(P.wy[2], ah, av); av = __fmaf_rn(P.wy[3], ah, av);
+        alpha_i = trunc_i(__fmul_rn(av, P.factor));
+    }
+
+    RawRow<SBITS> cur, nxt;
+    fused_load<L>(P, fz, xs, yo_begin - 1, cur);
+
+    for (int k = yo_begin - 1; k <= yo_end; k++) {
+        if (k < yo_end) fused_load<L>(P, fz, xs, k + 1, nxt);
+        // ---- extra (halo) column for the warp's outer lanes ------------------------
+        f2 E[3] = {0ull, 0ull, 0ull};
+        if (!TAPS2 && need_extra) {
+            const int H = P.src.h;
+            const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+            const int rc = min(max(k, 0), (H >> 1) - 1);
+            const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+            unsigned a, b, u, v;
+            const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch + xe * SB;
+            const uint8_t *qb = py + (size_t)rb * P.src.pl[0].pitch + xe * SB;
+            if (SBITS == 8) { a = *qa; b = *qb; }
+            else { a = *reinterpret_cast<const uint16_t *>(qa); b = *reinterpret_cast<const uint16_t *>(qb); }
+            if (L == L_NV12) {
+                const uint8_t *qc = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * 2 * SB;
+                if (SBITS == 8) { u = qc[0]; v = qc[1]; }
+                else { u = reinterpret_cast<const uint16_t *>(qc)[0]; v = reinterpret_cast<const uint16_t *>(qc)[1]; }
+            } else {
+                const uint8_t *qu = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * SB;
+                const uint8_t *qv = P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + (xe >> 1) * SB;
+                if (SBITS == 8) { u = *qu; v = *qv; }
+                else { u = *reinterpret_cast<const uint16_t *>(qu); v = *reinterpret_cast<const uint16_t *>(qv); }
+            }
+            float fu, fv;
+            upk(add2(pk(__uint_as_float(0x4B000000u | u), __uint_as_float(0x4B000000u | v)), bc(CB)), fu, fv);
+            ChromaTerms t = chroma_terms<SPARSE>(fu, fv, P.M);
+            fused_column<SBITS, SPARSE>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, E);
+        }
+        // ---- colour conversion of the 8x2 block ------------------------------------
+        float yt[8], yb[8], um[4], vm[4];
+        fused_unpack<L>(cur, yt, yb, um, vm);
+        f2 C[8][3];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float fu, fv;
+            upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+            ChromaTerms t = chroma_terms<SPARSE>(fu, fv, P.M);
+            fused_column<SBITS, SPARSE>(yt[2 * j], yb[2 * j], t, P, C[2 * j]);
+            fused_column<SBITS, SPARSE>(yt[2 * j + 1], yb[2 * j + 1], t, P, C[2 * j + 1]);
+        }
+        // ---- halo columns ------------------------------------------------------------
+        f2 PL[3] = {0ull, 0ull, 0ull}, PR[3] = {0ull, 0ull, 0ull};
+        if (!TAPS2) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                f2 up = shfl_up2(C[7][c]), dn = shfl_dn2(C[0][c]);
+                PL[c] = ledge ? C[0][c] : (lane == 0 ? E[c] : up);
+                PR[c] = redge ? C[7][c] : (lane == 31 ? E[c] : dn);
+            }
+        }
+        // ---- horizontal pass (packed over the row pair) ----------------------------
+        float ht[4][3], hbm[4][3];
+#pragma unroll
+        for (int xo = 0; xo < 4; xo++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                f2 p0 = xo == 0 ? PL[c] : C[2 * xo - 1][c];
+                f2 p3 = xo == 3 ? PR[c] : C[2 * xo + 2][c];
+                f2 h = hpass<TAPS2>(P.wx, p0, C[2 * xo][c], C[2 * xo + 1][c], p3);
+                upk(h, ht[xo][c], hbm[xo][c]);
+            }
+        // ---- vertical pass: finish output row k-1, start output row k ---------------
+        const int yo = k - 1;
+        if (yo >= yo_begin && active) {
+            int o[4][3];
+#pragma unroll
+            for (int xo = 0; xo < 4; xo++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float v = TAPS2 ? acc[xo][c] : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
+                    o[xo][c] = trunc_i(__fmul_rn(v, P.factor));
+                    if (P.wrap) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
+                }
+            constexpr bool SW = dst_swap(DST);
+            uint8_t *pd = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + (size_t)yo * P.dst.pl[0].pitch
+                        + (size_t)(x0 >> 1) * dst_bpp(DST);
+#define CH(i, c) o[i][SW ? 2 - (c) : (c)]
+            if (DST == D_RGB24 || DST == D_BGR24) {
+                stg32(pd,     pack4_u8(CH(0, 0), CH(0, 1), CH(0, 2), CH(1, 0)));
+                stg32(pd + 4, pack4_u8(CH(1, 1), CH(1, 2), CH(2, 0), CH(2, 1)));
+                stg32(pd + 8, pack4_u8(CH(2, 2), CH(3, 0), CH(3, 1), CH(3, 2)));
+            } else if (DST == D_RGBA || DST == D_BGRA) {
+                stg128(pd, make_uint4(pack4_u8(CH(0, 0), CH(0, 1), CH(0, 2), alpha_i), pack4_u8(CH(1, 0), CH(1, 1), CH(1, 2), alpha_i),
+                                      pack4_u8(CH(2, 0), CH(2, 1), CH(2, 2), alpha_i), pack4_u8(CH(3, 0), CH(3, 1), CH(3, 2), alpha_i)));
+            } else if (DST == D_RGB48 || DST == D_BGR48) {
+                stg64(pd,      make_uint2(pack2_u16(CH(0, 0), CH(0, 1)), pack2_u16(CH(0, 2), CH(1, 0))));
+                stg64(pd + 8,  make_uint2(pack2_u16(CH(1, 1), CH(1, 2)), pack2_u16(CH(2, 0), CH(2, 1))));
+                stg64(pd + 16, make_uint2(pack2_u16(CH(2, 2), CH(3, 0)), pack2_u16(CH(3, 1), CH(3, 2))));
+            } else {
+                stg128(pd, make_uint4(pack2_u16(CH(0, 0), CH(0, 1)), pack2_u16(CH(0, 2), alpha_i),
+                                      pack2_u16(CH(1, 0), CH(1, 1)), pack2_u16(CH(1, 2), alpha_i)));
+                stg128(pd + 16, make_uint4(pack2_u16(CH(2, 0), CH(2, 1)), pack2_u16(CH(2, 2), alpha_i),
+                                           pack2_u16(CH(3, 0), CH(3, 1)), pack2_u16(CH(3, 2), alpha_i)));
+            }
+#undef CH
+        }
+#pragma unroll
+        for (int xo = 0; xo < 4; xo++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float t = __fmul_rn(P.wy[1], ht[xo][c]);
+                if (!TAPS2) t = __fmaf_rn(P.wy[0], hb_prev[xo][c], t);
+                t = __fmaf_rn(P.wy[2], hbm[xo][c], t);
+                acc[xo][c] = t;
+                hb_prev[xo][c] = hbm[xo][c];
+            }
+        cur = nxt;
+    }
+}
+
+}  // namespace gmatb
