@@ -15,6 +15,11 @@
 #include "../../include/gmat_b200.h"
 #include "../../include/gmat_b200_sws.h"
 
+/* av_log lives in libavutil, which is always present when this object is linked into
+ * ffmpeg-gpu; weak so that the library can also be loaded on its own by the ABI tests. */
+#pragma weak av_log
+#define LOG(...) do { if (av_log) av_log(__VA_ARGS__); } while (0)
+
 void ff_yuv2rgb_init_tables_cuda(SwsContext *c)
 {
     /* reference: set_mat_yuv2rgb_cuda / set_mat_rgb2yuv_cuda(c->cspace) into process-global
@@ -28,7 +33,7 @@ int ff_sws_init_swscale_cuda(SwsContext *c)
     GmatbSws *g = gmatb_sws_create(c->srcW, c->srcH, (int)c->srcFormat, c->dstW, c->dstH, (int)c->dstFormat,
                                    c->flags, c->param, (int)c->cspace);
     if (!g) {
-        av_log(c, AV_LOG_ERROR, "gmat_b200: unsupported conversion %dx%d fmt %d -> %dx%d fmt %d\n",
+        LOG(c, AV_LOG_ERROR, "gmat_b200: unsupported conversion %dx%d fmt %d -> %dx%d fmt %d\n",
                c->srcW, c->srcH, (int)c->srcFormat, c->dstW, c->dstH, (int)c->dstFormat);
         return AVERROR(EINVAL);
     }
@@ -48,7 +53,7 @@ int ff_swscale_cuda(SwsContext *c, const uint8_t *src[], int srcStride[], int sr
     gmatb_sws_set_stream(g, (void *)c->cuda_stream);
     ret = gmatb_sws_scale(g, (const uint8_t *const *)src, srcStride, (uint8_t *const *)dst, dstStride);
     if (ret < 0) {
-        av_log(c, AV_LOG_ERROR, "gmat_b200: scale failed (%d, cuda %d: %s)\n", ret,
+        LOG(c, AV_LOG_ERROR, "gmat_b200: scale failed (%d, cuda %d: %s)\n", ret,
                gmatb_last_cuda_error(), gmatb_last_cuda_error_string());
         return AVERROR_EXTERNAL;
     }

@@ -175,13 +175,12 @@ def main(out):
                          dw, dh, d1.linesize[0], sw, sh, param)
                 host = dst1.numpy()
                 G[f"o2_{algo}_{pn}_y8_{sw}x{sh}_{dw}x{dh}"] = np.ascontiguousarray(dst1.plane_view(host, 0, 0)).reshape(-1)
-                # 16-bit plane
-                src2 = FrameBatch(FMT.YUV420P16LE, sw, sh, 1, device=dev); src2.fill_lcg(seed=91 + sw + dw)
-                dst2 = FrameBatch(FMT.YUV420P16LE, dw, dh, 1, device=dev)
+                # 16-bit plane: luma launch of the p016le kernel (plane 0 = 1 x u16, plane 1 = 2 x u16)
+                src2 = FrameBatch(FMT.P016LE, sw, sh, 1, device=dev); src2.fill_lcg(seed=91 + sw + dw)
+                dst2 = FrameBatch(FMT.P016LE, dw, dh, 1, device=dev)
                 s2, d2 = src2.image(), dst2.image()
-                planes = [(s2.data[0], s2.linesize[0], sw, sh, 16, 1), (s2.data[1], s2.linesize[1], cw, chh, 16, 1),
-                          (s2.data[2], s2.linesize[2], cw, chh, 16, 1)]
-                o2_scale(L2, f"Subsample_{algo}_yuv420p16le_yuv420p16le", planes, [d2.data[0], d2.data[1], d2.data[2]],
+                planes = [(s2.data[0], s2.linesize[0], sw, sh, 16, 1), (s2.data[1], s2.linesize[1], cw, chh, 16, 2)]
+                o2_scale(L2, f"Subsample_{algo}_p016le_p016le", planes, [d2.data[0], d2.data[1]],
                          dw, dh, d2.linesize[0], sw, sh, param)
                 host = dst2.numpy()
                 G[f"o2_{algo}_{pn}_y16_{sw}x{sh}_{dw}x{dh}"] = np.ascontiguousarray(dst2.plane_view(host, 0, 0)).reshape(-1)

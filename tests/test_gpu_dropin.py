@@ -1,0 +1,80 @@
+"""-m gpu: the drop-in itself.  The REFERENCE's own libswscale.so (CPU objects, built by
+oracle/refbuild without its cuda/ objects) is loaded on top of libgmat_b200.so + libgmat_b200_sws.so and
+driven through its public API exactly like metrans/app/CSwscale.c: sws_getContext(...,
+SWS_HWACCEL_CUDA) -> sws_setCudaStream -> sws_scale -> sws_freeContext_cuda."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gmat_b200 as g
+from gmat_b200 import FMT, SWS, FrameBatch, SwsContext
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFSO = os.path.join(ROOT, "oracle", "_ref", "libref_swscale_cpu.so")
+vp, ci = C.c_void_p, C.c_int
+
+
+@pytest.fixture(scope="module")
+def refsws():
+    if not os.path.exists(REFSO):
+        pytest.skip("oracle/_ref/libref_swscale_cpu.so not built")
+    g.lib()
+    C.CDLL(os.path.join(ROOT, "gmat_b200", "libgmat_b200_sws.so"), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(REFSO, mode=C.RTLD_GLOBAL)
+    L.sws_getContext.restype = vp
+    L.sws_getContext.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, vp, C.POINTER(C.c_double)]
+    L.sws_scale.restype = ci
+    L.sws_scale.argtypes = [vp, C.POINTER(vp), C.POINTER(ci), ci, ci, C.POINTER(vp), C.POINTER(ci)]
+    L.sws_setCudaStream.argtypes = [vp, vp]
+    L.sws_freeContext_cuda.argtypes = [vp]
+    return L
+
+
+def call(L, ctx, src, dst):
+    si, di = src.image(), dst.image()
+    sp = (vp * 4)(*[si.data[i] for i in range(4)]); ss = (ci * 4)(*[si.linesize[i] for i in range(4)])
+    dp = (vp * 4)(*[di.data[i] for i in range(4)]); ds = (ci * 4)(*[di.linesize[i] for i in range(4)])
+    return L.sws_scale(ctx, sp, ss, 0, src.h, dp, ds)
+
+
+@pytest.mark.parametrize("sfmt,dfmt", [(FMT.NV12, FMT.RGB24), (FMT.YUV420P, FMT.BGRA), (FMT.RGB24, FMT.NV12), (FMT.NV12, FMT.YUV420P),
+                                       (FMT.RGB24, FMT.BGR24), (FMT.NV12, FMT.P010LE), (FMT.NV12, FMT.RGBPF32LE)])
+def test_unscaled_through_reference_sws_scale(dev, refsws, sfmt, dfmt):
+    w, h = 320, 180
+    src = FrameBatch(sfmt, w, h, 1, device=dev); src.fill_lcg(seed=1)
+    ctx = refsws.sws_getContext(w, h, sfmt, w, h, dfmt, SWS.HWACCEL_CUDA | SWS.BICUBIC, None, None, None)
+    assert ctx, "reference sws_getContext returned NULL"
+    out = FrameBatch(dfmt, w, h, 1, device=dev)
+    st = torch.cuda.Stream()
+    refsws.sws_setCudaStream(ctx, st.cuda_stream)
+    assert call(refsws, ctx, src, out) == 0            # the reference's CUDA path returns 0
+    st.synchronize()
+    exp = FrameBatch(dfmt, w, h, 1, device=dev)
+    SwsContext(w, h, sfmt, w, h, dfmt).scale(src, exp); torch.cuda.synchronize()
+    assert torch.equal(out.buf, exp.buf)
+    refsws.sws_freeContext_cuda(ctx)
+
+
+@pytest.mark.parametrize("flags,param", [(SWS.BICUBIC, None), (SWS.LANCZOS, None), (SWS.BILINEAR, None), (SWS.BICUBIC, (0.75, 0.0))])
+def test_scaled_through_reference_sws_scale(dev, refsws, flags, param):
+    sw, sh, dw, dh = 1280, 720, 640, 360
+    src = FrameBatch(FMT.NV12, sw, sh, 1, device=dev); src.fill_lcg(seed=2)
+    pp = (C.c_double * 2)(*param) if param else None
+    ctx = refsws.sws_getContext(sw, sh, FMT.NV12, dw, dh, FMT.RGB24, SWS.HWACCEL_CUDA | flags, None, None, pp)
+    assert ctx
+    out = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev)
+    assert call(refsws, ctx, src, out) == 0
+    torch.cuda.synchronize()
+    exp = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev)
+    SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.RGB24, SWS.HWACCEL_CUDA | flags, param[:1] if param else None).scale(src, exp)
+    torch.cuda.synchronize()
+    assert torch.equal(out.buf, exp.buf)
+    refsws.sws_freeContext_cuda(ctx)
+
+
+def test_unsupported_pair_makes_reference_getcontext_fail(refsws):
+    assert not refsws.sws_getContext(64, 48, FMT.RGBPF32LE, 32, 24, FMT.NV12, SWS.HWACCEL_CUDA, None, None, None)

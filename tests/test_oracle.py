@@ -1,0 +1,179 @@
+"""CPU tests of the oracle (oracle/gmat_oracle.c): known-answer tests from SURVEY 8a and the
+golden vectors produced by the REFERENCE's own CUDA kernels on a B200
+(tests/golden/make_golden.py -> tests/golden/reference_gpu_golden.npz)."""
+import re
+
+import numpy as np
+import pytest
+
+import orc
+from gmat_b200 import FMT, FrameBatch
+
+# SURVEY 8a KAT: IEEE-754 bit patterns of the 9 floats the reference uploads
+KAT_Y2R = {
+    0: "3f950a85 00000000 3fd0f4a3 3f950a85 becd296b bf54df0d 3f950a85 40040ce8 00000000",
+    1: "3f950a85 00000000 3feab5bd 3f950a85 be5f5a23 bf0b8a1d 3f950a85 400a47c4 00000000",
+    4: "3f950a85 00000000 3fd0a854 3f950a85 bec5d883 bf5431b2 3f950a85 4004a586 00000000",
+    7: "3f950a85 00000000 3feae386 3f950a85 be871a9c bf0e1290 3f950a85 40081314 00000000",
+    9: "3f959f90 00000000 3fdca26f 3f959f90 be44f7c5 bf2af9ba 3f959f90 400cc029 00000000",
+}
+KAT_R2Y = {
+    0: "3e8379bf 3f010ea0 3dc882e1 be14646e be91a9a6 3edbdbdc 3edbdbdc beb81ab5 bd8f049c",
+    1: "3e3af7cb 3f1d3e37 3d7dfb1d bdc9847b bea97abd 3edbdbdc 3edbdbdc bec7b2f5 bd214738",
+    4: "3e83ea51 3f01b77a 3dc179cc be14382d be91bfc5 3edbdbdc 3edbdbdc beb94f40 bd8a326d",
+    7: "3e3a70b6 3f1a1efc 3d990591 bdcc34cb bea8cea8 3edbdbdc 3edbdbdc bec395c7 bd4230a6",
+    9: "3e6620f3 3f147bf8 3d4fca56 bdf4a2b7 be9dd82d 3edb00db 3edb00db bec963a2 bd0ce9bc",
+}
+
+
+def bits(m):
+    return " ".join("%08x" % x for x in m.view(np.uint32))
+
+
+@pytest.mark.parametrize("cs", sorted(KAT_Y2R))
+def test_matrix_kat(cs):
+    assert bits(orc.matrix_yuv2rgb(cs)) == KAT_Y2R[cs]
+    assert bits(orc.matrix_rgb2yuv(cs)) == KAT_R2Y[cs]
+    # colourspaces 5 and 6 (BT470BG, SMPTE170M) are the default matrix
+    if cs == 0:
+        for alias in (5, 6, 2, 3):
+            assert bits(orc.matrix_yuv2rgb(alias)) == KAT_Y2R[0]
+
+
+def test_matrix_matches_reference_upload(golden):
+    """what the reference's set_mat_*_cuda actually put into constant memory on the B200"""
+    for cs in (0, 1, 4, 5, 6, 7, 9):
+        assert bits(orc.matrix_yuv2rgb(cs)) == bits(golden[f"mat_y2r_{cs}"])
+        assert bits(orc.matrix_rgb2yuv(cs)) == bits(golden[f"mat_r2y_{cs}"])
+
+
+def test_product_matrix_equals_oracle():
+    import gmat_b200 as g
+    for cs in (0, 1, 4, 5, 6, 7, 9, 10):
+        assert bits(g.csc_matrix_yuv2rgb(cs)) == bits(orc.matrix_yuv2rgb(cs))
+        assert bits(g.csc_matrix_rgb2yuv(cs)) == bits(orc.matrix_rgb2yuv(cs))
+
+
+def test_worked_example():
+    """(Y,U,V) = (81,90,240), default matrix"""
+    src = FrameBatch(FMT.NV12, 2, 2, 1)
+    host = np.zeros(src.frame_bytes, np.uint8)
+    src.plane_view(host, 0, 0)[...] = 81
+    src.plane_view(host, 0, 1)[0, 0] = 90; src.plane_view(host, 0, 1)[0, 1] = 240
+    src.upload(host)
+    dst = FrameBatch(FMT.RGB24, 2, 2, 1)
+    orc.yuv2rgb(src, dst)
+    m = orc.matrix_yuv2rgb(0).astype(np.float64)
+    fy, fu, fv = 65.0, -38.0, 112.0
+    exp = [int(min(max(m[3 * i] * fy + m[3 * i + 1] * fu + m[3 * i + 2] * fv, 0), 255)) for i in range(3)]
+    assert list(dst.payload()[:3]) == exp == [255, 0, 0] or list(dst.payload()[:3]) == exp
+
+
+def test_norm_two_term_is_exact():
+    """FFMA(j,khi,RN(j*klo)) == RN(j/max) for every sample value (gmat_b200/csrc/resample_core.cuh)"""
+    assert orc.orc().orc_check_norm(0) == 0
+    assert orc.orc().orc_check_norm(1) == 0
+
+
+def test_bicubic_coefficients_closed_form():
+    # exact 2:1: fx = 0.5 for every output; A = -0.75 gives dyadic weights, default A = 0 a 2x2 box
+    co, po = orc.filter_table(orc.ALGO["bicubic"], 3840, 1920, -0.75)
+    assert np.all(co == np.array([-0.09375, 0.59375, 0.59375, -0.09375], np.float32))
+    assert np.all(po == 2 * np.arange(1920) - 1)
+    co, _ = orc.filter_table(orc.ALGO["bicubic"], 3840, 1920, 0.0)
+    assert np.all(co == np.array([0, 0.5, 0.5, 0], np.float32))
+    # partition of unity to 1 ulp at arbitrary ratios
+    co, _ = orc.filter_table(orc.ALGO["bicubic"], 1920, 1281, -0.5)
+    assert np.abs(co.sum(1) - 1).max() < 3e-7
+
+
+def _case(name):
+    m = re.match(r"o1_(\w+?)_(\w+?)_(\d+)x(\d+)(?:_cs(\d))?$", name)
+    return m
+
+
+FMTS = {"nv12": FMT.NV12, "yuv420p": FMT.YUV420P, "p010": FMT.P010LE, "p016": FMT.P016LE, "yuv420p10": FMT.YUV420P10LE,
+        "yuv420p16": FMT.YUV420P16LE, "rgb24": FMT.RGB24, "bgr24": FMT.BGR24, "rgba": FMT.RGBA, "bgra": FMT.BGRA,
+        "rgba64": FMT.RGBA64LE, "bgra64": FMT.BGRA64LE}
+SEEDS = {"nv12_rgb": lambda w, h: 1234 + w * 131 + h}
+
+
+def test_oracle_vs_reference_csc_golden(golden):
+    """every O1 golden vector: the reference's libgpuscale kernels vs the CPU restatement"""
+    import ctypes as C
+    n = 0
+    for name in golden.files:
+        m = _case(name)
+        if not m or name.endswith("_crc"):
+            continue
+        sname, dname, w, h, cs = m.group(1), m.group(2), int(m.group(3)), int(m.group(4)), int(m.group(5) or 0)
+        sfmt, dfmt = FMTS[sname], FMTS[dname]
+        src = FrameBatch(sfmt, w, h, 1)
+        dst = FrameBatch(dfmt, w, h, 1)
+        yuv_s = sname in ("nv12", "yuv420p", "p010", "p016")
+        yuv_d = dname in ("nv12", "yuv420p", "p010", "p016", "yuv420p10", "yuv420p16")
+        if yuv_s and not yuv_d:
+            src.fill_lcg(seed=(99 + w) if sname == "p016" else (1234 + w * 131 + h))
+            orc.yuv2rgb(src, dst, cs)
+        elif not yuv_s and yuv_d:
+            src.fill_lcg(seed=4321 + w)
+            orc.rgb2yuv(src, dst, cs)
+        elif yuv_s and yuv_d:
+            src.fill_lcg(seed=(555 + w) if sname == "nv12" else (777 + w))
+            s, d = src.image(), dst.image()
+            orc.orc().orc_yuv2yuv(C.byref(s), C.byref(d))
+        else:
+            src.fill_lcg(seed=888 + w)
+            s, d = src.image(), dst.image()
+            orc.orc().orc_rgb24tobgr24(C.byref(s), C.byref(d))
+        got, exp = dst.payload(), golden[name]
+        assert got.shape == exp.shape, name
+        bad = int((got != exp).sum())
+        assert bad == 0, f"{name}: {bad} of {got.size} bytes differ from the reference kernel's output"
+        n += 1
+    assert n >= 100
+
+
+def _o2_cases(golden):
+    for name in golden.files:
+        m = re.match(r"o2_(Bicubic|Lanczos|Nearest)_(def|[\d.]+)_(rgb0|y8|y16)_(\d+)x(\d+)_(\d+)x(\d+)$", name)
+        if m:
+            yield name, m.group(1), m.group(2), m.group(3), tuple(int(x) for x in m.groups()[3:])
+
+
+def test_oracle_vs_reference_resample_golden(golden):
+    """O2 golden vectors (the reference's scale_cuda kernels) vs the CPU restatement of R-B.
+    Bicubic / nearest coefficient tables are computed on the CPU (bit-exact restatement);
+    Lanczos tables need the GPU's __sinf and are covered by the -m gpu tests."""
+    import ctypes as C
+    L = orc.orc()
+    n = 0
+    for name, algo, pn, kind, (sw, sh, dw, dh) in _o2_cases(golden):
+        if algo == "Lanczos":
+            continue
+        A = 0.0 if pn == "def" else -float(pn)
+        a = orc.ALGO["bicubic"] if algo == "Bicubic" else orc.ALGO["nearest"]
+        cx, px = orc.filter_table(a, sw, dw, A)
+        cy, py = orc.filter_table(a, sh, dh, A)
+        ra = 1 if algo == "Nearest" else 0
+        if kind == "rgb0":
+            src = FrameBatch(FMT.RGBA, sw, sh, 1); src.fill_lcg(seed=31 + sw + dw)
+            dst = FrameBatch(FMT.RGBA, dw, dh, 1)
+            s, d = src.image(), dst.image()
+            L.orc_resample_packed(s.data[0], s.linesize[0], sw, sh, d.data[0], d.linesize[0], dw, dh, 4, 0,
+                                  orc.fptr(cx), orc.iptr(px), orc.fptr(cy), orc.iptr(py), ra, 1)
+            got = dst.payload()
+        else:
+            b16 = kind == "y16"
+            fmt = FMT.YUV420P16LE if b16 else FMT.YUV420P
+            src = FrameBatch(fmt, sw, sh, 1); src.fill_lcg(seed=(91 if b16 else 77) + sw + dw)
+            dst = FrameBatch(fmt, dw, dh, 1)
+            s, d = src.image(), dst.image()
+            L.orc_resample_packed(s.data[0], s.linesize[0], sw, sh, d.data[0], d.linesize[0], dw, dh, 1, int(b16),
+                                  orc.fptr(cx), orc.iptr(px), orc.fptr(cy), orc.iptr(py), ra, 1)
+            got = np.ascontiguousarray(dst.plane_view(dst.numpy(), 0, 0)).reshape(-1)
+        exp = golden[name]
+        bad = int((got != exp).sum())
+        assert bad == 0, f"{name}: {bad} of {got.size} bytes differ from the reference scale_cuda output"
+        n += 1
+    assert n >= 40
