@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(256) yuv2rgb_kernel(Img src, Img dst, Mat9 M, 
     for (int j = 0; j < 4; j++) {
         float fu, fv;
         upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-        ChromaTerms t = chroma_terms<SPARSE>(fu, fv, M);
+        ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, M);
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
-            csc_pair_i<SPARSE>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
-                               b[rr][2 * j], b[rr][2 * j + 1]);
+            csc_pair_i<SPARSE, SBITS == 16>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
+                                            b[rr][2 * j], b[rr][2 * j + 1]);
         }
     }
     constexpr int BPP = dst_bpp(DST);
@@ -245,12 +245,12 @@ __global__ void __launch_bounds__(256) yuv2rgb_planar_f32_kernel(Img src, Img ds
     for (int j = 0; j < 4; j++) {
         float fu, fv;
         upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-        ChromaTerms t = chroma_terms<SPARSE>(fu, fv, M);
+        ChromaTerms t = chroma_terms<SPARSE, true>(fu, fv, M);     // planar kernels of the reference: FMA form
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
-            csc_pair_i<SPARSE>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
-                               b[rr][2 * j], b[rr][2 * j + 1]);
+            csc_pair_i<SPARSE, true>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
+                                     b[rr][2 * j], b[rr][2 * j + 1]);
         }
     }
     const float sh[3] = {sr, sg, sb};

@@ -36,17 +36,33 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
 // Products of one chroma sample with the matrix (shared by the 2x2 luma block).
 struct ChromaTerms {
     float t1r, t1g, t1b;   // m[1]*fu, m[4]*fu, m[7]*fu
-    float t2r, t2g, t2b;   // m[2]*fv, m[5]*fv, m[8]*fv
+    float t2r, t2g, t2b;   // m[2]*fv, m[5]*fv, m[8]*fv   (FADD form only)
+    float fv;              // (FMA form only)
 };
 
 // SPARSE: m[1] == 0 and m[8] == 0 (true for every matrix the reference builds,
 // yuv2rgb_cuda.cu:820-824).  FFMA(fy,m0,+-0) == FMUL(fy,m0) and x + (+-0) == x,
 // so skipping the zero terms cannot change a result bit (up to the sign of zero,
 // which the truncation discards).
-template <bool SPARSE>
+//
+// The reference's kernels come in TWO roundings of the same expression, because nvcc
+// contracts them differently (SASS of oracle/_ref/libref_gpuscale.so):
+//   FADD form  r = FADD(FFMA(fy,mA,FMUL(fu,mB)), FMUL(fv,mC))   yuv2rgb_odd_kernel / yuv02rgb_odd_kernel:
+//                                                                NV12/I420 -> packed 8/16-bit rgb
+//   FMA  form  r = FFMA(fv,mC, FFMA(fy,mA,FMUL(fu,mB)))          yuv2rgb_kernel / yuv2rgb_planar_kernel:
+//                                                                P010/P016 sources and planar-float output
+// FMAFORM selects which one a kernel reproduces.
+template <bool SPARSE, bool FMAFORM = false>
 __device__ __forceinline__ ChromaTerms chroma_terms(float fu, float fv, const Mat9 &M) {
     ChromaTerms t;
     float a, b;
+    t.fv = fv;
+    if (FMAFORM) {
+        t.t1g = __fmul_rn(fu, M.m[4]); t.t1b = __fmul_rn(fu, M.m[7]);
+        t.t1r = SPARSE ? 0.f : __fmul_rn(fu, M.m[1]);
+        t.t2r = t.t2g = t.t2b = 0.f;
+        return t;
+    }
     upk(mul2(pk(fu, fv), pk(M.m[4], M.m[5])), a, b); t.t1g = a; t.t2g = b;
     upk(mul2(pk(fu, fv), pk(M.m[7], M.m[2])), a, b); t.t1b = a; t.t2r = b;
     if (SPARSE) { t.t1r = 0.f; t.t2b = 0.f; }
@@ -58,7 +74,7 @@ __device__ __forceinline__ ChromaTerms chroma_terms(float fu, float fv, const Ma
 
 // Two horizontally adjacent pixels (same chroma): fy2 = (y0-low, y1-low).
 // Outputs are the UNCLAMPED float results of the reference chain.
-template <bool SPARSE>
+template <bool SPARSE, bool FMAFORM = false>
 __device__ __forceinline__ void csc_pair_f(f2 fy2, const ChromaTerms &t, const Mat9 &M,
                                            f2 &r, f2 &g, f2 &b) {
     // NB: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both
@@ -67,20 +83,26 @@ __device__ __forceinline__ void csc_pair_f(f2 fy2, const ChromaTerms &t, const M
     // the addend is m[1] itself (== 0.0f, checked on the host), so this is
     // FFMA2(fy, m0, 0) = RN(fy*m0), exactly the reference's FFMA(fy, m0, +-0).
     f2 xr = fma2(fy2, bc(M.m[0]), bc(SPARSE ? M.m[1] : t.t1r));
-    r = add2(xr, bc(t.t2r));
     f2 xg = fma2(fy2, bc(M.m[3]), bc(t.t1g));
-    g = add2(xg, bc(t.t2g));
     f2 xb = fma2(fy2, bc(M.m[6]), bc(t.t1b));
-    b = SPARSE ? xb : add2(xb, bc(t.t2b));
+    if (FMAFORM) {
+        r = fma2(bc(t.fv), bc(M.m[2]), xr);
+        g = fma2(bc(t.fv), bc(M.m[5]), xg);
+        b = SPARSE ? xb : fma2(bc(t.fv), bc(M.m[8]), xb);     // FFMA(fv, 0, x) == x
+    } else {
+        r = add2(xr, bc(t.t2r));
+        g = add2(xg, bc(t.t2g));
+        b = SPARSE ? xb : add2(xb, bc(t.t2b));
+    }
 }
 
 // ... and truncated to integers (sign-magnitude for negatives: any negative value
 // is a large negative s32, which the saturating packs clamp to 0).
-template <bool SPARSE>
+template <bool SPARSE, bool FMAFORM = false>
 __device__ __forceinline__ void csc_pair_i(f2 fy2, const ChromaTerms &t, const Mat9 &M,
                                            int &r0, int &r1, int &g0, int &g1, int &b0, int &b1) {
     f2 r, g, b;
-    csc_pair_f<SPARSE>(fy2, t, M, r, g, b);
+    csc_pair_f<SPARSE, FMAFORM>(fy2, t, M, r, g, b);
     const f2 z = bc(GMATB_TWO_M149);
     upki(mul2_rz(r, z), r0, r1);
     upki(mul2_rz(g, z), g0, g1);

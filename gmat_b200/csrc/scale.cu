@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "scale_fused.cuh"
+#include "scale_fused_lut.cuh"
 #include "scale_generic.cuh"
 
 namespace gmatb {
@@ -211,6 +212,49 @@ static int launch_fused_d(int dc, bool taps2, dim3 g, cudaStream_t st, const Fus
     return set_cuda_error(cudaGetLastError());
 }
 
+template <int L>
+static int launch_fused_lut(int dc, bool taps2, int grid, cudaStream_t st, const FusedLutParams &Q) {
+    cudaError_t e = cudaSuccess;
+#define GO(D, T) do { \
+        static bool attr_done = false; \
+        if (!attr_done) { e = cudaFuncSetAttribute(fused_csc_scale2_lut_kernel<L, D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES); attr_done = true; } \
+        if (e == cudaSuccess) fused_csc_scale2_lut_kernel<L, D, T><<<grid, 512, LUT_BYTES, st>>>(Q); } while (0)
+#define GD(D) do { if (taps2) GO(D, true); else GO(D, false); } while (0)
+    switch (dc) {
+    case D_RGB24: GD(D_RGB24); break;
+    case D_BGR24: GD(D_BGR24); break;
+    case D_RGBA:  GD(D_RGBA); break;
+    case D_BGRA:  GD(D_BGRA); break;
+    default: return GMATB_ERR_UNSUPPORTED;
+    }
+#undef GD
+#undef GO
+    if (e != cudaSuccess) return set_cuda_error(e);
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// range of the colour-conversion results for 8-bit input under matrix M
+static void csc_range(const Mat9 &M, float *lo, float *hi) {
+    *lo = 1e30f; *hi = -1e30f;
+    for (int c = 0; c < 3; c++) {
+        const float *m = M.m + 3 * c;
+        float mn = 0.f, mx = 0.f;
+        const float a[3][2] = {{-16.f, 239.f}, {-128.f, 127.f}, {-128.f, 127.f}};
+        for (int k = 0; k < 3; k++) { mn += std::min(m[k] * a[k][0], m[k] * a[k][1]); mx += std::max(m[k] * a[k][0], m[k] * a[k][1]); }
+        *lo = std::min(*lo, mn); *hi = std::max(*hi, mx);
+    }
+}
+
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
         if (((uintptr_t)a.pl[i].p | (uintptr_t)a.pl[i].pitch | (uintptr_t)a.pl[i].bstride) & (al - 1)) return false;
@@ -245,6 +289,29 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     nb = std::max(1, std::min(nb, (c->dstH + 7) / 8));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
+    // 8-bit sources with enough work: the persistent shared-memory-table kernel (scale_fused_lut.cuh)
+    if (bits == 8 && !(c->flags & GMATB_SWS_NO_LUT)) {
+        float lo, hi;
+        csc_range(c->M, &lo, &hi);
+        const int nsm = sm_count();
+        const long long items = (long long)warps_x * nb * batch;
+        if (lo > -(float)LUT_FIRST + 2.f && hi < (float)(LUT_N - LUT_FIRST) - 2.f && items >= 4LL * nsm) {
+            // fewer, longer bands: the persistent CTAs balance the queue themselves
+            long long want2 = (long long)nsm * 16 * 6;
+            int nb2 = (int)((want2 + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
+            nb2 = std::max(1, std::min(nb2, (c->dstH + 7) / 8));
+            FusedLutParams Q;
+            Q.f = P;
+            Q.f.band = (c->dstH + nb2 - 1) / nb2;
+            Q.nbands = (c->dstH + Q.f.band - 1) / Q.f.band;
+            Q.warps_x = warps_x; Q.batch = batch; Q.rmin = lo; Q.rmax = hi;
+            const long long total = (long long)warps_x * Q.nbands * batch;
+            const int grid = (int)std::min<long long>(nsm, (total + 15) / 16);
+            int rc2 = semi ? launch_fused_lut<L_NV12>(dc, c->taps2, grid, c->stream, Q) : launch_fused_lut<L_I420>(dc, c->taps2, grid, c->stream, Q);
+            *done = (rc2 == 0);
+            return rc2;
+        }
+    }
     dim3 g(warps_x, nb, batch);
     int rc;
     if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, g, c->stream, P);

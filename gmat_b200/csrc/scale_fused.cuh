@@ -112,7 +112,7 @@ template <int SBITS, bool SPARSE>
 __device__ __forceinline__ void fused_column(float ytm, float ybm, const ChromaTerms &t, const Fused2Params &P, f2 (&out)[3]) {
     constexpr float YB = -(GMATB_MAGIC + (SBITS == 8 ? 16.f : 4096.f));
     f2 r, g, b;
-    csc_pair_f<SPARSE>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
+    csc_pair_f<SPARSE, SBITS == 16>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
     out[0] = quant_norm2(r, P.nk); out[1] = quant_norm2(g, P.nk); out[2] = quant_norm2(b, P.nk);
 }
 
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params
             }
             float fu, fv;
             upk(add2(pk(__uint_as_float(0x4B000000u | u), __uint_as_float(0x4B000000u | v)), bc(CB)), fu, fv);
-            ChromaTerms t = chroma_terms<SPARSE>(fu, fv, P.M);
+            ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
             fused_column<SBITS, SPARSE>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, E);
         }
         // ---- colour conversion of the 8x2 block ------------------------------------
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params
         for (int j = 0; j < 4; j++) {
             float fu, fv;
             upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-            ChromaTerms t = chroma_terms<SPARSE>(fu, fv, P.M);
+            ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
             fused_column<SBITS, SPARSE>(yt[2 * j], yb[2 * j], t, P, C[2 * j]);
             fused_column<SBITS, SPARSE>(yt[2 * j + 1], yb[2 * j + 1], t, P, C[2 * j + 1]);
         }

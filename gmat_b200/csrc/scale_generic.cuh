@@ -80,9 +80,16 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
             const float fy = (float)(int)y - low, fu = (float)(int)u - mid, fv = (float)(int)v - mid;
             // scalar form of csc_pair_f (same IEEE operations)
             const float *m = P.M.m;
-            float r = __fadd_rn(__fmaf_rn(fy, m[0], __fmul_rn(fu, m[1])), __fmul_rn(fv, m[2]));
-            float g = __fadd_rn(__fmaf_rn(fy, m[3], __fmul_rn(fu, m[4])), __fmul_rn(fv, m[5]));
-            float b = __fadd_rn(__fmaf_rn(fy, m[6], __fmul_rn(fu, m[7])), __fmul_rn(fv, m[8]));
+            float r, g, b;
+            if (SBITS == 16) {   // FMA form (the reference's P016 template), see csc_core.cuh
+                r = __fmaf_rn(fv, m[2], __fmaf_rn(fy, m[0], __fmul_rn(fu, m[1])));
+                g = __fmaf_rn(fv, m[5], __fmaf_rn(fy, m[3], __fmul_rn(fu, m[4])));
+                b = __fmaf_rn(fv, m[8], __fmaf_rn(fy, m[6], __fmul_rn(fu, m[7])));
+            } else {
+                r = __fadd_rn(__fmaf_rn(fy, m[0], __fmul_rn(fu, m[1])), __fmul_rn(fv, m[2]));
+                g = __fadd_rn(__fmaf_rn(fy, m[3], __fmul_rn(fu, m[4])), __fmul_rn(fv, m[5]));
+                b = __fadd_rn(__fmaf_rn(fy, m[6], __fmul_rn(fu, m[7])), __fmul_rn(fv, m[8]));
+            }
             float rgb[3] = {r, g, b};
             for (int c = 0; c < 3; c++) {
                 float j = __fadd_rn(__fadd_rz(rgb[c], GMATB_MAGIC), -GMATB_MAGIC);   // trunc for r >= 0

@@ -126,11 +126,16 @@ void orc_matrix_rgb2yuv(int cspace, float m[9])
 /* ------------------------------------------------------------------ colour conversion
  * yuv2rgb_for_pixel (yuv2rgb_cuda.cu:72-106) as compiled: t1 = FMUL(fu,mB); t2 = FMUL(fv,mC);
  * x = FFMA(fy,mA,t1); r = FADD(x,t2); r<0 -> 0; min(r,max); F2I.U32.TRUNC. */
-static float csc_chain(float fy, float fu, float fv, const float *row)
+/* Two roundings exist in the reference, because nvcc contracts the same source expression
+ * differently per kernel (SASS of oracle/_ref/libref_gpuscale.so):
+ *   fma_form 0  yuv2rgb_odd_kernel / yuv02rgb_odd_kernel (NV12, I420 -> packed rgb):  FADD(FFMA(fy,mA,t1), FMUL(fv,mC))
+ *   fma_form 1  yuv2rgb_kernel (P010/P016) and yuv2rgb_planar_kernel (planar float):  FFMA(fv,mC, FFMA(fy,mA,t1)) */
+static float csc_chain(float fy, float fu, float fv, const float *row, int fma_form)
 {
     const float t1 = fu * row[1];
-    const float t2 = fv * row[2];
     const float x = fmaf(fy, row[0], t1);
+    if (fma_form) return fmaf(fv, row[2], x);
+    const float t2 = fv * row[2];
     return x + t2;
 }
 static unsigned quantise(float r, float maxf)
@@ -139,14 +144,17 @@ static unsigned quantise(float r, float maxf)
     if (r > maxf) r = maxf;         /* FMNMX */
     return (unsigned)r;             /* truncation */
 }
-static void yuv_to_rgb_q(unsigned Y, unsigned U, unsigned V, int b16, const float m[9], unsigned rgb[3])
+static void yuv_to_rgb_q2(unsigned Y, unsigned U, unsigned V, int b16, const float m[9], unsigned rgb[3], int fma_form)
 {
     const int low = b16 ? 4096 : 16, mid = b16 ? 32768 : 128;
     const float maxf = b16 ? 65535.0f : 255.0f;
     const float fy = (float)((int)Y - low), fu = (float)((int)U - mid), fv = (float)((int)V - mid);
-    for (int c = 0; c < 3; c++) rgb[c] = quantise(csc_chain(fy, fu, fv, m + 3 * c), maxf);
+    for (int c = 0; c < 3; c++) rgb[c] = quantise(csc_chain(fy, fu, fv, m + 3 * c, fma_form), maxf);
 }
-
+static void yuv_to_rgb_q(unsigned Y, unsigned U, unsigned V, int b16, const float m[9], unsigned rgb[3])
+{
+    yuv_to_rgb_q2(Y, U, V, b16, m, rgb, b16);      /* 16-bit sources: the P016 template's form */
+}
 static void put_rgb(uint8_t *p, int fmt, int src16, const unsigned rgb[3])
 {
     unsigned c[3] = {rgb[0], rgb[1], rgb[2]};
@@ -190,7 +198,7 @@ int orc_yuv2rgb_planar_f32(const GmatbImage *s, const GmatbImage *d, const float
             for (int x = 0; x < s->width; x++) {
                 unsigned Y, U, V, rgb[3];
                 get_yuv(s, f, x, y, &Y, &U, &V);
-                yuv_to_rgb_q(Y, U, V, 0, m, rgb);
+                yuv_to_rgb_q2(Y, U, V, 0, m, rgb, 1);        /* yuv2rgb_planar_kernel: FMA form */
                 for (int c = 0; c < 3; c++) {
                     float *q = (float *)((uint8_t *)plane(d, c, f) + (size_t)y * d->linesize[c]) + x;
                     *q = ((float)rgb[c] - (shift ? shift[c] : 0.0f)) / norm;

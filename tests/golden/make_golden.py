@@ -117,6 +117,12 @@ def main(out):
             o1_convert(L, "rgb2yuv_cuda", src, dst, w, h)
             G[f"o1_rgb24_nv12_{w}x{h}_cs{cs}"] = dst.payload()
     L.set_mat_yuv2rgb_cuda(0); L.set_mat_rgb2yuv_cuda(0)
+    # NV12 -> planar float (even sizes; the planar launcher skips odd edges)
+    for (w, h) in ((64, 48), (2, 2), (130, 6)):
+        src = FrameBatch(FMT.NV12, w, h, 1, device=dev); src.fill_lcg(seed=1234 + w * 131 + h)
+        dst = FrameBatch(FMT.RGBPF32LE, w, h, 1, device=dev)
+        o1_convert(L, "yuv2rgb_cuda", src, dst, w, h)
+        G[f"o1_nv12_rgbpf32_{w}x{h}"] = dst.payload()
     # P016 -> RGBA64 / BGRA64 (undispatched template, even sizes)
     for (w, h) in ((64, 48), (2, 2), (130, 6)):
         src = FrameBatch(FMT.P016LE, w, h, 1, device=dev)
@@ -169,8 +175,7 @@ def main(out):
                 dst1 = FrameBatch(FMT.YUV420P, dw, dh, 1, device=dev)
                 s1, d1 = src1.image(), dst1.image()
                 cw, chh = (sw + 1) // 2, (sh + 1) // 2
-                planes = [(s1.data[0], s1.linesize[0], sw, sh, 8, 1), (s1.data[1], s1.linesize[1], cw, chh, 8, 1),
-                          (s1.data[2], s1.linesize[2], cw, chh, 8, 1)]
+                planes = [(s1.data[0], s1.linesize[0], sw, sh, 8, 1)]     # the luma launch only reads texture 0
                 o2_scale(L2, f"Subsample_{algo}_yuv420p_yuv420p", planes, [d1.data[0], d1.data[1], d1.data[2]],
                          dw, dh, d1.linesize[0], sw, sh, param)
                 host = dst1.numpy()
@@ -179,7 +184,7 @@ def main(out):
                 src2 = FrameBatch(FMT.P016LE, sw, sh, 1, device=dev); src2.fill_lcg(seed=91 + sw + dw)
                 dst2 = FrameBatch(FMT.P016LE, dw, dh, 1, device=dev)
                 s2, d2 = src2.image(), dst2.image()
-                planes = [(s2.data[0], s2.linesize[0], sw, sh, 16, 1), (s2.data[1], s2.linesize[1], cw, chh, 16, 2)]
+                planes = [(s2.data[0], s2.linesize[0], sw, sh, 16, 1)]
                 o2_scale(L2, f"Subsample_{algo}_p016le_p016le", planes, [d2.data[0], d2.data[1]],
                          dw, dh, d2.linesize[0], sw, sh, param)
                 host = dst2.numpy()

@@ -84,6 +84,7 @@ def test_exhaustive_yuv_triples_vs_reference(dev):
 def test_p016_vs_reference_template(dev, w, h):
     """P016 -> RGBA64/BGRA64: the undispatched p0162color64 template of the reference (:612-618)"""
     src = FrameBatch(FMT.P016LE, w, h, 1, device=dev); src.fill_lcg(seed=3 * w + h)
+    o1().set_mat_yuv2rgb_cuda(0); torch.cuda.synchronize()
     for order, dfmt in ((0, FMT.RGBA64LE), (1, FMT.BGRA64LE)):
         ref = FrameBatch(dfmt, w, h, 1, device=dev)
         si, ri = src.image(), ref.image()
