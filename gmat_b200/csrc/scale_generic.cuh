@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
             int v;
             if (RA) v = (int)fminf(fmaxf(rintf(t), 0.f), P.vmax);
             else {
-                v = trunc_i(__fmul_rn(t, P.factor));
+                // fmaxf(NaN, -1) = -1: a NaN (the reference's Lanczos coefficients are 0/0 when the phase
+                // is ~1e-8 but not 0: all four __sinf taps flush to zero) stores 0, like cvt.rzi.u32.f32(NaN)
+                v = trunc_i(fmaxf(__fmul_rn(t, P.factor), -1.0f));
                 v = P.wrap ? (max(v, 0) & smax) : clamp_i(v, smax);
             }
             o[c] = v;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
                 float av = __fmul_rn(w.y, ah);
                 av = __fmaf_rn(w.x, ah, av); av = __fmaf_rn(w.z, ah, av); av = __fmaf_rn(w.w, ah, av);
                 if (RA) a = (int)fminf(fmaxf(rintf(av), 0.f), P.vmax);
-                else { a = trunc_i(__fmul_rn(av, P.factor)); a = P.wrap ? (max(a, 0) & smax) : clamp_i(a, smax); }
+                else { a = trunc_i(fmaxf(__fmul_rn(av, P.factor), -1.0f)); a = P.wrap ? (max(a, 0) & smax) : clamp_i(a, smax); }
             }
             const bool sw = dst_swap(P.dst_code);
             const int c0 = sw ? o[2] : o[0], c2 = sw ? o[0] : o[2];

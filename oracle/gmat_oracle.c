@@ -404,7 +404,7 @@ static unsigned finish(float v, int b16, int ra, int wrap)
     const int maxv = b16 ? 65535 : 255;
     if (ra) { float r = rintf(v); if (r < 0) r = 0; if (r > (float)maxv) r = (float)maxv; return (unsigned)r; }
     float o = v * (b16 ? 65535.0f : 255.0f);
-    if (o < 0.0f) return 0;          /* cvt.rzi.u32.f32 saturates negatives to 0 */
+    if (!(o >= 0.0f)) return 0;      /* cvt.rzi.u32.f32: negatives and NaN -> 0 */
     unsigned u = (unsigned)o;
     if (wrap) return u & (unsigned)maxv;   /* the reference stores the low bits */
     return u > (unsigned)maxv ? (unsigned)maxv : u;

@@ -107,6 +107,15 @@ def test_oracle_vs_reference_csc_golden(golden):
         if not m or name.endswith("_crc"):
             continue
         sname, dname, w, h, cs = m.group(1), m.group(2), int(m.group(3)), int(m.group(4)), int(m.group(5) or 0)
+        if dname == "rgbpf32":
+            src = FrameBatch(FMT.NV12, w, h, 1); src.fill_lcg(seed=1234 + w * 131 + h)
+            dst = FrameBatch(FMT.RGBPF32LE, w, h, 1)
+            mm = orc.matrix_yuv2rgb(0); sh = np.zeros(3, np.float32)
+            s, d = src.image(), dst.image()
+            orc.orc().orc_yuv2rgb_planar_f32(C.byref(s), C.byref(d), orc.fptr(mm), 255.0, orc.fptr(sh))
+            assert np.array_equal(dst.payload(), golden[name]), name
+            n += 1
+            continue
         sfmt, dfmt = FMTS[sname], FMTS[dname]
         src = FrameBatch(sfmt, w, h, 1)
         dst = FrameBatch(dfmt, w, h, 1)
@@ -128,6 +137,19 @@ def test_oracle_vs_reference_csc_golden(golden):
             orc.orc().orc_rgb24tobgr24(C.byref(s), C.byref(d))
         got, exp = dst.payload(), golden[name]
         assert got.shape == exp.shape, name
+        if (sname, dname) in (("nv12", "yuv420p"), ("yuv420p", "nv12")):
+            # reference defect: the 8-bit (de)interleave launchers round their grid DOWN
+            # (yuv2yuv_cuda.cu:293,304 "(height + 3) / 4 / 2" blocks of 8 rows, "(width + 31) / 32 / 2" of 64
+            # columns), so trailing rows/columns are never written.  Compare what the reference covers.
+            rows = min(h, ((h + 3) // 4 // 2) * 8); cols = min(w, ((w + 31) // 32 // 2) * 64)
+            assert cols == w, name
+            if rows < h:
+                keep = np.zeros(0, bool)
+                for p_, (off, pitch, prow, rb) in enumerate(dst.planes):
+                    lim = rows if p_ == 0 else rows // 2
+                    keep = np.concatenate([keep, (np.arange(prow)[:, None] < lim).repeat(rb, 1).reshape(-1)])
+                assert not exp[~keep].any(), name          # untouched (still zero) in the reference's output
+                got, exp = got[keep], exp[keep]
         bad = int((got != exp).sum())
         assert bad == 0, f"{name}: {bad} of {got.size} bytes differ from the reference kernel's output"
         n += 1
