@@ -7,43 +7,51 @@
 // reference's texture fetch returns, p = RN(j/255), clamped -- 4 FMA-pipe operations per
 // sample, two of which (.sat) have no packed form.  Here that step leaves the FP32 pipe:
 //
-//   m   = FADD2.RZ(r, 2^23)                    bits(m) = 0x4B000000 + trunc(r)
-//   p   = LUT[bits(m) - 0x4B000000]            one LDS per sample
+//   m    = FADD2.RZ(4r, magic)                 bits(m) = const + floor(r)
+//   addr = SHF(bits, lane)                      one ALU op
+//   p    = LDS [addr]                           one shared-memory load per sample
 //
-// The table holds RN(clamp(j,0,255)/255) for every index the CSC can produce (negative
-// results land below 0x4B000000 in half-unit steps and read 0.0; values above 255 read 1.0),
-// so the clamp is free.  To make the lookup conflict-free for ANY data it is replicated
-// once per lane: word address = index*32 + lane, i.e. each lane only ever touches its own
-// shared-memory bank -- exactly one wavefront per LDS whatever the pixel values are.
-// 1152 entries x 32 lanes x 4 B = 144 KB of the SM's 227 KB, which is why this kernel is
-// PERSISTENT: one 512-thread CTA per SM builds the table once and its 16 warps then pull
-// (frame, band, strip) work items from a grid-stride queue until the batch is done.
+// The table holds RN(clamp(j,0,255)/255) for every value floor(r) can take (negative results
+// read 0.0, results above 255 read 1.0), so the clamp is free.  To make the lookup
+// conflict-free for ANY data it is replicated once per lane: word address = index*32 + lane,
+// i.e. each lane only ever touches its own shared-memory bank -- exactly one wavefront per
+// LDS whatever the pixel values are.  1024 entries x 32 lanes x 4 B = 128 KB of the SM's
+// 227 KB, which is why this kernel is PERSISTENT: one 512-thread CTA per SM builds the table
+// once and its 16 warps then pull (frame, band, strip) work items from a grid-stride queue
+// until the batch is done.
 #pragma once
 #include "scale_fused.cuh"
 
 namespace gmatb {
 
-#define LUT_BIAS  512                  // added to the magic constant: every sum stays >= 2^23 (ulp 1)
-#define LUT_FIRST 256                  // first table entry = index 256  <=>  floor(r) = -256
-#define LUT_N     896                  // entries: floor(r) in [-256, 640)
-#define LUT_BYTES (LUT_N * 32 * 4)
-#define LUT_MAGIC (GMATB_MAGIC + (float)LUT_BIAS)
+#define LUT_FIRST 384                  // table entry 0  <=>  floor(r) = -384  (B of BT.2020 reaches -299)
+#define LUT_N     1024                 // entries: floor(r) in [-384, 640)
+#define LUT_BYTES (LUT_N * 32 * 4 + 128)
 
 struct FusedLutParams {
-    Fused2Params f;
+    Fused2Params f;                // f.M holds 4 x the CSC matrix (see below)
     int warps_x, nbands, batch;    // work-item grid
-    float rmin, rmax;              // range of CSC results for this matrix (host-computed; must fit the table)
 };
 
-// p(top), p(bottom) of one colour component of one column.
-//   m = RZ(r + 2^23 + 512): the sum is >= 2^23, so its ulp is 1 and bits(m) = 0x4B000200 + floor(r)
-//   (negative r read the zero entries below index 512, r > 255 the 1.0 entries: the clamp is free)
-//   shared address = lane_base + (bits << 7)   [32-bit wrap-around arithmetic; one LEA]
-__device__ __forceinline__ f2 lut_norm2(f2 r, unsigned lane_base) {
-    const f2 m = add2_rz(r, bc(LUT_MAGIC));
+// p(top), p(bottom) of one colour component of one column, from r4 = 4*r.
+//
+// The colour-conversion chain is run with the matrix scaled by 4 (a power of two: every
+// intermediate is exactly 4x the reference's, roundings included), so that the truncating
+// add can use the magic constant 2^25, whose bit pattern 0x4C000000 has NO bits inside the
+// 25 positions that survive a left shift by 7:
+//   m    = RZ(4r + 2^25 + 4*(384 + base/128))       ulp(2^25) = 4  ->  m = 2^25 + 4*(floor(r) + 384 + base/128)
+//   bits = 0x4C000000 + floor(r) + 384 + base/128
+//   addr = funnel-shift-left((bits : lane*4 << 25), 7) = (floor(r)+384)*128 + base + lane*4
+// i.e. the absolute shared-memory address of this lane's copy of the entry, in ONE ALU
+// instruction (SHF) -- no integer multiply-add on the FP32 pipe, no clamp: negative results
+// read the 0.0 entries, results above 255 the 1.0 entries.
+__device__ __forceinline__ f2 lut_norm2(f2 r4, f2 magic2, unsigned lane_hi) {
+    const f2 m = add2_rz(r4, magic2);
     int b0, b1;
     upki(m, b0, b1);
-    const unsigned a0 = lane_base + ((unsigned)b0 << 7), a1 = lane_base + ((unsigned)b1 << 7);
+    unsigned a0, a1;
+    asm("shf.l.wrap.b32 %0, %1, %2, 7;" : "=r"(a0) : "r"(lane_hi), "r"(b0));
+    asm("shf.l.wrap.b32 %0, %1, %2, 7;" : "=r"(a1) : "r"(lane_hi), "r"(b1));
     float p0, p1;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p0) : "r"(a0));
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p1) : "r"(a1));
@@ -52,26 +60,30 @@ __device__ __forceinline__ f2 lut_norm2(f2 r, unsigned lane_base) {
 
 template <bool SPARSE>
 __device__ __forceinline__ void lut_column(float ytm, float ybm, const ChromaTerms &t, const Fused2Params &P,
-                                           unsigned lut_lane, f2 (&out)[3]) {
+                                           f2 magic2, unsigned lane_hi, f2 (&out)[3]) {
     constexpr float YB = -(GMATB_MAGIC + 16.f);
     f2 r, g, b;
-    csc_pair_f<SPARSE>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
-    out[0] = lut_norm2(r, lut_lane); out[1] = lut_norm2(g, lut_lane); out[2] = lut_norm2(b, lut_lane);
+    csc_pair_f<SPARSE>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);      // P.M = 4*M  ->  4r
+    out[0] = lut_norm2(r, magic2, lane_hi); out[1] = lut_norm2(g, magic2, lane_hi); out[2] = lut_norm2(b, magic2, lane_hi);
 }
 
 template <int L, int DST, bool TAPS2>
 __global__ void __launch_bounds__(512, 1) fused_csc_scale2_lut_kernel(const FusedLutParams Q) {
-    extern __shared__ float lut[];          // [LUT_N][32]
+    extern __shared__ float lut_raw[];
     const Fused2Params &P = Q.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // ---- build the table (once per CTA): entry e <-> floor(r) = e - 256 ---------------------
+    // 128-byte aligned table base (so that base/128 can ride in the magic constant)
+    const unsigned raw = (unsigned)__cvta_generic_to_shared(lut_raw);
+    const unsigned base = (raw + 127u) & ~127u;
+    float *lut = lut_raw + ((base - raw) >> 2);         // [LUT_N][32]
+    // ---- build the table (once per CTA): entry e <-> floor(r) = e - LUT_FIRST ---------------------
     for (int i = threadIdx.x; i < LUT_N * 32; i += blockDim.x) {
-        const int j = min(max((i >> 5) - 256, 0), 255);
+        const int j = min(max((i >> 5) - LUT_FIRST, 0), 255);
         lut[i] = __fdiv_rn((float)j, 255.0f);          // what the texture unit returns for texel j
     }
     __syncthreads();
-    // (bits << 7) mod 2^32 = 0x80000000 + (512 + floor(r)) * 128 for bits = 0x4B000000 + 512 + floor(r)
-    const unsigned lut_lane = (unsigned)__cvta_generic_to_shared(lut) + lane * 4u - 0x80000000u - (unsigned)LUT_FIRST * 128u;
+    const f2 magic2 = bc(33554432.0f + 4.0f * (float)(LUT_FIRST + (base >> 7)));   // 2^25 + 4*(LUT_FIRST + base/128), exact
+    const unsigned lane_hi = (unsigned)(lane * 4) << 25;
 
     const int W = P.src.w;
     constexpr float CB = -(GMATB_MAGIC + 128.f);
@@ -124,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) fused_csc_scale2_lut_kernel(const Fuse
                 float fu, fv;
                 upk(add2(pk(__uint_as_float(0x4B000000u | u), __uint_as_float(0x4B000000u | v)), bc(CB)), fu, fv);
                 ChromaTerms t = chroma_terms<true>(fu, fv, P.M);
-                lut_column<true>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, lut_lane, E);
+                lut_column<true>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, magic2, lane_hi, E);
             }
             float yt[8], yb[8], um[4], vm[4];
             fused_unpack<L>(cur, yt, yb, um, vm);
@@ -134,8 +146,8 @@ __global__ void __launch_bounds__(512, 1) fused_csc_scale2_lut_kernel(const Fuse
                 float fu, fv;
                 upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
                 ChromaTerms t = chroma_terms<true>(fu, fv, P.M);
-                lut_column<true>(yt[2 * j], yb[2 * j], t, P, lut_lane, C[2 * j]);
-                lut_column<true>(yt[2 * j + 1], yb[2 * j + 1], t, P, lut_lane, C[2 * j + 1]);
+                lut_column<true>(yt[2 * j], yb[2 * j], t, P, magic2, lane_hi, C[2 * j]);
+                lut_column<true>(yt[2 * j + 1], yb[2 * j + 1], t, P, magic2, lane_hi, C[2 * j + 1]);
             }
             f2 PL[3] = {0ull, 0ull, 0ull}, PR[3] = {0ull, 0ull, 0ull};
             if (!TAPS2) {

@@ -116,9 +116,9 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
 __device__ __forceinline__ f2 quant_norm2(f2 r, const NormK &k) {
     const f2 m = add2_rz(r, bc(GMATB_MAGIC));
     const f2 j = add2(m, bc(-GMATB_MAGIC));
+    const f2 t = mul2(j, bc(k.klo));          // feeds an fma addend: ptxas cannot contract it further
     float j0, j1, t0, t1;
-    upk(j, j0, j1);
-    t0 = __fmul_rn(j0, k.klo); t1 = __fmul_rn(j1, k.klo);
+    upk(j, j0, j1); upk(t, t0, t1);
     return pk(fma_sat(j0, k.khi, t0), fma_sat(j1, k.khi, t1));
 }
 

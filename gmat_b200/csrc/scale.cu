@@ -7,7 +7,6 @@
 #include <cstring>
 #include <vector>
 #include "scale_fused.cuh"
-#include "scale_fused_lut.cuh"
 #include "scale_generic.cuh"
 
 namespace gmatb {
@@ -184,52 +183,44 @@ static NormK norm_k(int bits) {
     return k;
 }
 
+static int fused_minb() {      // tuning knob (resident warps per SM the register allocation must allow)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GMATB_FUSED_MINB"); v = e ? atoi(e) : 20; }
+    return v;
+}
+
 template <int L, int SBITS, int DST>
-static void launch_fused_t(bool taps2, dim3 g, cudaStream_t st, const Fused2Params &P) {
-    if (taps2) fused_csc_scale2_kernel<L, SBITS, DST, true, true><<<g, 32, 0, st>>>(P);
-    else       fused_csc_scale2_kernel<L, SBITS, DST, true, false><<<g, 32, 0, st>>>(P);
+static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused2Params &P) {
+#define K(T, W, M) fused_csc_scale2_kernel<L, SBITS, DST, T, W, M><<<g, 32, 0, st>>>(P)
+    if (wrap) { if (taps2) K(true, true, 16); else K(false, true, 16); return; }
+    if (L == L_NV12 && SBITS == 8 && DST == D_RGB24) {       // the headline instantiation carries the tuning variants
+        const int m = fused_minb();
+        if (taps2) { if (m >= 32) K(true, false, 32); else if (m >= 28) K(true, false, 28); else if (m >= 24) K(true, false, 24); else if (m >= 20) K(true, false, 20); else K(true, false, 16); }
+        else       { if (m >= 32) K(false, false, 32); else if (m >= 28) K(false, false, 28); else if (m >= 24) K(false, false, 24); else if (m >= 20) K(false, false, 20); else K(false, false, 16); }
+        return;
+    }
+    if (taps2) K(true, false, 16); else K(false, false, 16);
+#undef K
 }
 template <int L, int SBITS>
-static int launch_fused_d(int dc, bool taps2, dim3 g, cudaStream_t st, const Fused2Params &P) {
+static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused2Params &P) {
     if (SBITS == 8) {
         switch (dc) {
-        case D_RGB24: launch_fused_t<L, SBITS, D_RGB24>(taps2, g, st, P); break;
-        case D_BGR24: launch_fused_t<L, SBITS, D_BGR24>(taps2, g, st, P); break;
-        case D_RGBA:  launch_fused_t<L, SBITS, D_RGBA>(taps2, g, st, P); break;
-        case D_BGRA:  launch_fused_t<L, SBITS, D_BGRA>(taps2, g, st, P); break;
+        case D_RGB24: launch_fused_t<L, SBITS, D_RGB24>(taps2, wrap, g, st, P); break;
+        case D_BGR24: launch_fused_t<L, SBITS, D_BGR24>(taps2, wrap, g, st, P); break;
+        case D_RGBA:  launch_fused_t<L, SBITS, D_RGBA>(taps2, wrap, g, st, P); break;
+        case D_BGRA:  launch_fused_t<L, SBITS, D_BGRA>(taps2, wrap, g, st, P); break;
         default: return GMATB_ERR_UNSUPPORTED;
         }
     } else {
         switch (dc) {
-        case D_RGB48:  launch_fused_t<L, SBITS, D_RGB48>(taps2, g, st, P); break;
-        case D_BGR48:  launch_fused_t<L, SBITS, D_BGR48>(taps2, g, st, P); break;
-        case D_RGBA64: launch_fused_t<L, SBITS, D_RGBA64>(taps2, g, st, P); break;
-        case D_BGRA64: launch_fused_t<L, SBITS, D_BGRA64>(taps2, g, st, P); break;
+        case D_RGB48:  launch_fused_t<L, SBITS, D_RGB48>(taps2, wrap, g, st, P); break;
+        case D_BGR48:  launch_fused_t<L, SBITS, D_BGR48>(taps2, wrap, g, st, P); break;
+        case D_RGBA64: launch_fused_t<L, SBITS, D_RGBA64>(taps2, wrap, g, st, P); break;
+        case D_BGRA64: launch_fused_t<L, SBITS, D_BGRA64>(taps2, wrap, g, st, P); break;
         default: return GMATB_ERR_UNSUPPORTED;
         }
     }
-    count_launch();
-    return set_cuda_error(cudaGetLastError());
-}
-
-template <int L>
-static int launch_fused_lut(int dc, bool taps2, int grid, cudaStream_t st, const FusedLutParams &Q) {
-    cudaError_t e = cudaSuccess;
-#define GO(D, T) do { \
-        static bool attr_done = false; \
-        if (!attr_done) { e = cudaFuncSetAttribute(fused_csc_scale2_lut_kernel<L, D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES); attr_done = true; } \
-        if (e == cudaSuccess) fused_csc_scale2_lut_kernel<L, D, T><<<grid, 512, LUT_BYTES, st>>>(Q); } while (0)
-#define GD(D) do { if (taps2) GO(D, true); else GO(D, false); } while (0)
-    switch (dc) {
-    case D_RGB24: GD(D_RGB24); break;
-    case D_BGR24: GD(D_BGR24); break;
-    case D_RGBA:  GD(D_RGBA); break;
-    case D_BGRA:  GD(D_BGRA); break;
-    default: return GMATB_ERR_UNSUPPORTED;
-    }
-#undef GD
-#undef GO
-    if (e != cudaSuccess) return set_cuda_error(e);
     count_launch();
     return set_cuda_error(cudaGetLastError());
 }
@@ -241,18 +232,6 @@ static int sm_count() {
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
-}
-
-// range of the colour-conversion results for 8-bit input under matrix M
-static void csc_range(const Mat9 &M, float *lo, float *hi) {
-    *lo = 1e30f; *hi = -1e30f;
-    for (int c = 0; c < 3; c++) {
-        const float *m = M.m + 3 * c;
-        float mn = 0.f, mx = 0.f;
-        const float a[3][2] = {{-16.f, 239.f}, {-128.f, 127.f}, {-128.f, 127.f}};
-        for (int k = 0; k < 3; k++) { mn += std::min(m[k] * a[k][0], m[k] * a[k][1]); mx += std::max(m[k] * a[k][0], m[k] * a[k][1]); }
-        *lo = std::min(*lo, mn); *hi = std::max(*hi, mx);
-    }
 }
 
 static bool planes_aligned(const Img &a, int np, int al) {
@@ -289,33 +268,11 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     nb = std::max(1, std::min(nb, (c->dstH + 7) / 8));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
-    // 8-bit sources with enough work: the persistent shared-memory-table kernel (scale_fused_lut.cuh)
-    if (bits == 8 && !(c->flags & GMATB_SWS_NO_LUT)) {
-        float lo, hi;
-        csc_range(c->M, &lo, &hi);
-        const int nsm = sm_count();
-        const long long items = (long long)warps_x * nb * batch;
-        if (lo > -(float)LUT_FIRST + 2.f && hi < (float)(LUT_N - LUT_FIRST) - 2.f && items >= 4LL * nsm) {
-            // fewer, longer bands: the persistent CTAs balance the queue themselves
-            long long want2 = (long long)nsm * 16 * 6;
-            int nb2 = (int)((want2 + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
-            nb2 = std::max(1, std::min(nb2, (c->dstH + 7) / 8));
-            FusedLutParams Q;
-            Q.f = P;
-            Q.f.band = (c->dstH + nb2 - 1) / nb2;
-            Q.nbands = (c->dstH + Q.f.band - 1) / Q.f.band;
-            Q.warps_x = warps_x; Q.batch = batch; Q.rmin = lo; Q.rmax = hi;
-            const long long total = (long long)warps_x * Q.nbands * batch;
-            const int grid = (int)std::min<long long>(nsm, (total + 15) / 16);
-            int rc2 = semi ? launch_fused_lut<L_NV12>(dc, c->taps2, grid, c->stream, Q) : launch_fused_lut<L_I420>(dc, c->taps2, grid, c->stream, Q);
-            *done = (rc2 == 0);
-            return rc2;
-        }
-    }
     dim3 g(warps_x, nb, batch);
     int rc;
-    if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, g, c->stream, P);
-    else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, g, c->stream, P);
+    const bool wrap = P.wrap != 0;
+    if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
+    else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, wrap, g, c->stream, P);
     *done = (rc == 0);
     return rc;
 }

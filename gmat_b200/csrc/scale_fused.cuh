@@ -130,8 +130,9 @@ __device__ __forceinline__ f2 hpass(const float (&w)[4], f2 p0, f2 p1, f2 p2, f2
 
 // DST: D_* code from csc.cu (packed rgb).  TAPS2: the outer weights of both axes are
 // exactly zero (default bicubic, A = 0, at 2:1), FFMA(0, p, t) == t is skipped.
-template <int L, int SBITS, int DST, bool SPARSE, bool TAPS2>
-__global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params P) {
+template <int L, int SBITS, int DST, bool TAPS2, bool WRAP, int MINB>
+__global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2Params P) {
+    constexpr bool SPARSE = true;     // the host only selects this kernel for matrices with m[1] == m[8] == 0
     const int lane = threadIdx.x;
     const int W = P.src.w;
     const int x0 = (blockIdx.x * 32 + lane) * 8;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params
     RawRow<SBITS> cur, nxt;
     fused_load<L>(P, fz, xs, yo_begin - 1, cur);
 
+#pragma unroll 2
     for (int k = yo_begin - 1; k <= yo_end; k++) {
         if (k < yo_end) fused_load<L>(P, fz, xs, k + 1, nxt);
         // ---- extra (halo) column for the warp's outer lanes ------------------------
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(32) fused_csc_scale2_kernel(const Fused2Params
                 for (int c = 0; c < 3; c++) {
                     float v = TAPS2 ? acc[xo][c] : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
                     o[xo][c] = trunc_i(__fmul_rn(v, P.factor));
-                    if (P.wrap) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
+                    if (WRAP) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
                 }
             constexpr bool SW = dst_swap(DST);
             uint8_t *pd = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + (size_t)yo * P.dst.pl[0].pitch

@@ -89,9 +89,6 @@ extern "C" {
  * scale_cuda kernels' missing upper clamp (values >= 256 wrap modulo 256,
  * vf_scale_cuda.cu:1057-1071 + cvt.rzi) instead of saturating. */
 #define GMATB_SWS_PARITY_WRAP   0x40000000
-/* gmat_b200 extension bit: do not use the shared-memory-table variant of the fused kernel
- * (same results; A/B switch for tests and profiling). */
-#define GMATB_SWS_NO_LUT        0x20000000
 
 /* ---- interpolation / border codes of the filter layer (NVCV numbering:
  *      NVCV_INTERP_* / NVCV_BORDER_* as used by vf_rotate_nvcv.c:115-135 and
