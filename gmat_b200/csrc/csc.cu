@@ -278,6 +278,68 @@ __global__ void __launch_bounds__(256) yuv2rgb_planar_f32_kernel(Img src, Img ds
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// 8-sample / 4-sample vector row accesses (samples of 1 or 2 bytes)
+// ---------------------------------------------------------------------------
+template <int BYTES> __device__ __forceinline__ void load8(const uint8_t *p, unsigned (&o)[8]) {
+    if (BYTES == 1) {
+        uint2 w = ldg64(p);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { o[i] = (w.x >> (8 * i)) & 0xFFu; o[4 + i] = (w.y >> (8 * i)) & 0xFFu; }
+    } else {
+        uint4 w = ldg128(p);
+        o[0] = w.x & 0xFFFFu; o[1] = w.x >> 16; o[2] = w.y & 0xFFFFu; o[3] = w.y >> 16;
+        o[4] = w.z & 0xFFFFu; o[5] = w.z >> 16; o[6] = w.w & 0xFFFFu; o[7] = w.w >> 16;
+    }
+}
+template <int BYTES> __device__ __forceinline__ void store8(uint8_t *p, const unsigned (&v)[8]) {
+    if (BYTES == 1) {
+        stg64(p, make_uint2(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24), v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24)));
+    } else {
+        stg128(p, make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16)));
+    }
+}
+template <int BYTES> __device__ __forceinline__ void load4(const uint8_t *p, unsigned (&o)[4]) {
+    if (BYTES == 1) {
+        uint32_t w = ldg32(p);
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = (w >> (8 * i)) & 0xFFu;
+    } else {
+        uint2 w = ldg64(p);
+        o[0] = w.x & 0xFFFFu; o[1] = w.x >> 16; o[2] = w.y & 0xFFFFu; o[3] = w.y >> 16;
+    }
+}
+template <int BYTES> __device__ __forceinline__ void store4(uint8_t *p, const unsigned (&v)[4]) {
+    if (BYTES == 1) stg32(p, v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    else stg64(p, make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16)));
+}
+// chroma of a 4:2:0 tile (4 samples each of U and V), either layout
+template <int L, int BYTES>
+__device__ __forceinline__ void load_chroma4(const Img &s, long long fz, int cx, int cy, unsigned (&u)[4], unsigned (&v)[4]) {
+    if (L == L_NV12) {
+        unsigned t[8];
+        load8<BYTES>(s.pl[1].p + fz * s.pl[1].bstride + (size_t)cy * s.pl[1].pitch + (size_t)cx * 2 * BYTES, t);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { u[j] = t[2 * j]; v[j] = t[2 * j + 1]; }
+    } else {
+        load4<BYTES>(s.pl[1].p + fz * s.pl[1].bstride + (size_t)cy * s.pl[1].pitch + (size_t)cx * BYTES, u);
+        load4<BYTES>(s.pl[2].p + fz * s.pl[2].bstride + (size_t)cy * s.pl[2].pitch + (size_t)cx * BYTES, v);
+    }
+}
+template <int L, int BYTES>
+__device__ __forceinline__ void store_chroma4(const Img &d, long long fz, int cx, int cy, const unsigned (&u)[4], const unsigned (&v)[4]) {
+    if (L == L_NV12) {
+        unsigned t[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { t[2 * j] = u[j]; t[2 * j + 1] = v[j]; }
+        store8<BYTES>(d.pl[1].p + fz * d.pl[1].bstride + (size_t)cy * d.pl[1].pitch + (size_t)cx * 2 * BYTES, t);
+    } else {
+        store4<BYTES>(d.pl[1].p + fz * d.pl[1].bstride + (size_t)cy * d.pl[1].pitch + (size_t)cx * BYTES, u);
+        store4<BYTES>(d.pl[2].p + fz * d.pl[2].bstride + (size_t)cy * d.pl[2].pitch + (size_t)cx * BYTES, v);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // packed rgb -> yuv 4:2:0   (yuv2rgb_cuda.cu:653-739)
 // ---------------------------------------------------------------------------
@@ -290,7 +352,7 @@ __host__ __device__ constexpr bool srgb_is16(int s) { return s >= S_RGBA64; }
 // 16-bit rgb -> 8-bit yuv uses the high byte of each component (the reference
 // mis-reads every non-RGB24 source as RGB24, :748-762 -- not reproduced).
 template <int SRC, int L, int DBITS>
-__global__ void __launch_bounds__(256) rgb2yuv_kernel(Img src, Img dst, Mat9 M) {
+__global__ void __launch_bounds__(256) rgb2yuv_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     const int W = src.w, H = src.h;
@@ -302,7 +364,45 @@ __global__ void __launch_bounds__(256) rgb2yuv_kernel(Img src, Img dst, Mat9 M) 
     constexpr int DBS = DBITS / 8;
     const uint8_t *ps = src.pl[0].p + fz * src.pl[0].bstride;
 
+    const bool full = vec_ok && x0 + 8 <= W && y0 + 2 <= H;
     int cr[2][8], cg[2][8], cb[2][8];
+    if (full) {
+        // 128/64-bit row loads: 24 / 32 / 64 bytes per 8-pixel row
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uint8_t *row = ps + (size_t)(y0 + rr) * src.pl[0].pitch + (size_t)x0 * BPP;
+            unsigned a[8], b[8], c[8];
+            if (srgb_is16(SRC)) {
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    uint4 w = ldg128(row + 16 * h);
+                    a[2 * h] = w.x & 0xFFFFu; b[2 * h] = w.x >> 16; c[2 * h] = w.y & 0xFFFFu;
+                    a[2 * h + 1] = w.z & 0xFFFFu; b[2 * h + 1] = w.z >> 16; c[2 * h + 1] = w.w & 0xFFFFu;
+                }
+                if (DBITS == 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { a[i] >>= 8; b[i] >>= 8; c[i] >>= 8; }
+                }
+            } else if (BPP == 4) {
+                uint4 w0 = ldg128(row), w1 = ldg128(row + 16);
+                const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) { a[i] = w[i] & 0xFFu; b[i] = (w[i] >> 8) & 0xFFu; c[i] = (w[i] >> 16) & 0xFFu; }
+            } else {
+                uint2 q0 = ldg64(row), q1 = ldg64(row + 8), q2 = ldg64(row + 16);
+                const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    unsigned t[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { const int bi = 3 * i + k; t[k] = (w[bi >> 2] >> (8 * (bi & 3))) & 0xFFu; }
+                    a[i] = t[0]; b[i] = t[1]; c[i] = t[2];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) { cr[rr][i] = srgb_swap(SRC) ? c[i] : a[i]; cg[rr][i] = b[i]; cb[rr][i] = srgb_swap(SRC) ? a[i] : c[i]; }
+        }
+    } else
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         int yy = min(y0 + rr, H - 1);
@@ -326,6 +426,27 @@ __global__ void __launch_bounds__(256) rgb2yuv_kernel(Img src, Img dst, Mat9 M) 
         }
     }
     uint8_t *pdy = dst.pl[0].p + fz * dst.pl[0].bstride;
+    if (full) {
+        unsigned uu[4], vv[4];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            unsigned yv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                yv[i] = clamp_i(trunc_i(rgb2y_f((float)cr[rr][i], (float)cg[rr][i], (float)cb[rr][i], M, 0, LOW)), DMAX);
+            store8<DBS>(pdy + (size_t)(y0 + rr) * dst.pl[0].pitch + (size_t)x0 * DBS, yv);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int mr = (cr[0][2 * j] + cr[0][2 * j + 1] + cr[1][2 * j] + cr[1][2 * j + 1]) / 4;
+            const int mg = (cg[0][2 * j] + cg[0][2 * j + 1] + cg[1][2 * j] + cg[1][2 * j + 1]) / 4;
+            const int mb = (cb[0][2 * j] + cb[0][2 * j + 1] + cb[1][2 * j] + cb[1][2 * j + 1]) / 4;
+            uu[j] = clamp_i(trunc_i(rgb2y_f((float)mr, (float)mg, (float)mb, M, 1, MID)), DMAX);
+            vv[j] = clamp_i(trunc_i(rgb2y_f((float)mr, (float)mg, (float)mb, M, 2, MID)), DMAX);
+        }
+        store_chroma4<L, DBS>(dst, fz, x0 >> 1, y0 >> 1, uu, vv);
+        return;
+    }
 #pragma unroll
     for (int rr = 0; rr < 2; rr++)
 #pragma unroll
@@ -373,7 +494,7 @@ template <int SD, int DD> __device__ __forceinline__ unsigned conv_depth(unsigne
 }
 
 template <int SL, int SD, int DL, int DD>
-__global__ void __launch_bounds__(256) yuv2yuv_kernel(Img src, Img dst) {
+__global__ void __launch_bounds__(256) yuv2yuv_kernel(Img src, Img dst, int vec_ok) {
     constexpr int SB = SD == 8 ? 1 : 2, DB = DD == 8 ? 1 : 2;
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
@@ -381,6 +502,22 @@ __global__ void __launch_bounds__(256) yuv2yuv_kernel(Img src, Img dst) {
     if (x0 >= W || y0 >= H) return;
     const long long fz = blockIdx.z;
     const int cw = (W + 1) >> 1;
+    if (vec_ok && x0 + 8 <= W && y0 + 2 <= H) {
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            unsigned yv[8];
+            load8<SB>(src.pl[0].p + fz * src.pl[0].bstride + (size_t)(y0 + rr) * src.pl[0].pitch + (size_t)x0 * SB, yv);
+#pragma unroll
+            for (int i = 0; i < 8; i++) yv[i] = conv_depth<SD, DD>(yv[i]);
+            store8<DB>(dst.pl[0].p + fz * dst.pl[0].bstride + (size_t)(y0 + rr) * dst.pl[0].pitch + (size_t)x0 * DB, yv);
+        }
+        unsigned u[4], v[4];
+        load_chroma4<SL, SB>(src, fz, x0 >> 1, y0 >> 1, u, v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { u[j] = conv_depth<SD, DD>(u[j]); v[j] = conv_depth<SD, DD>(v[j]); }
+        store_chroma4<DL, DB>(dst, fz, x0 >> 1, y0 >> 1, u, v);
+        return;
+    }
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         if (y0 + rr >= H) break;
@@ -537,13 +674,15 @@ int yuv2rgb_planar_launch(const GmatbImage *src, const GmatbImage *dst, const Ma
 template <int SRC>
 static int launch_rgb2yuv_src(int dfmt, dim3 g, cudaStream_t st, const Img &s, const Img &d, const Mat9 &M) {
     dim3 b(32, 8);
+    const int np = (dfmt == GMATB_FMT_YUV420P) ? 3 : 2;
+    const int vec = aligned16(s, 1) && aligned16(d, np);
     switch (dfmt) {
-    case GMATB_FMT_NV12:    rgb2yuv_kernel<SRC, L_NV12, 8><<<g, b, 0, st>>>(s, d, M); break;
-    case GMATB_FMT_YUV420P: rgb2yuv_kernel<SRC, L_I420, 8><<<g, b, 0, st>>>(s, d, M); break;
+    case GMATB_FMT_NV12:    rgb2yuv_kernel<SRC, L_NV12, 8><<<g, b, 0, st>>>(s, d, M, vec); break;
+    case GMATB_FMT_YUV420P: rgb2yuv_kernel<SRC, L_I420, 8><<<g, b, 0, st>>>(s, d, M, vec); break;
     case GMATB_FMT_P010LE:
     case GMATB_FMT_P016LE:
         if (!srgb_is16(SRC)) return GMATB_ERR_UNSUPPORTED;
-        rgb2yuv_kernel<SRC, L_NV12, 16><<<g, b, 0, st>>>(s, d, M); break;
+        rgb2yuv_kernel<SRC, L_NV12, 16><<<g, b, 0, st>>>(s, d, M, vec); break;
     default: return GMATB_ERR_UNSUPPORTED;
     }
     count_launch();
@@ -589,7 +728,8 @@ int yuv2yuv_launch(const GmatbImage *src, const GmatbImage *dst, cudaStream_t st
     Img s, d;
     if (!to_img(src, &s, fmt_planes(src->format)) || !to_img(dst, &d, fmt_planes(dst->format))) return GMATB_ERR_INVAL;
     dim3 g = tile_grid(s.w, s.h, 2, src->batch), b(32, 8);
-#define K(SL, SD, DL, DD) yuv2yuv_kernel<SL, SD, DL, DD><<<g, b, 0, st>>>(s, d)
+    const int vec = aligned16(s, fmt_planes(src->format)) && aligned16(d, fmt_planes(dst->format));
+#define K(SL, SD, DL, DD) yuv2yuv_kernel<SL, SD, DL, DD><<<g, b, 0, st>>>(s, d, vec)
 #define KD(SL, SD, DL) do { if (dd == 8) K(SL, SD, DL, 8); else if (dd == 10) K(SL, SD, DL, 10); else K(SL, SD, DL, 16); } while (0)
 #define KL(SL, SD) do { if (dl == L_NV12) KD(SL, SD, L_NV12); else KD(SL, SD, L_I420); } while (0)
 #define KS(SL) do { if (sd == 8) KL(SL, 8); else if (sd == 10) KL(SL, 10); else KL(SL, 16); } while (0)

@@ -330,6 +330,57 @@ __global__ void __launch_bounds__(256) median_kernel(PImg s, PImg d, int kw, int
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// median, small windows (3x3, 5x5): pruned Batcher odd-even merge-sort SELECTION network on
+// u16x2 lanes (VIMNMX.U16x2 is a native Blackwell instruction): each thread ranks the windows
+// of TWO horizontally adjacent pixels at once, one network per channel, entirely in registers.
+// The comparator lists are generated by tools/gen_median_net.py (comparators that cannot reach
+// the median output are dropped: 40 min/max ops for 3x3, 202 for 5x5).
+// ---------------------------------------------------------------------------
+#define CS2(x, y)  do { const unsigned lo_ = __vminu2(x, y), hi_ = __vmaxu2(x, y); x = lo_; y = hi_; } while (0)
+#define CMIN(x, y) x = __vminu2(x, y)
+#define CMAX(x, y) x = __vmaxu2(x, y)
+#include "median_nets.inc"
+
+template <int BPP, int KW, int KH>
+__global__ void __launch_bounds__(256) median_net_kernel(PImg s, PImg d) {
+    extern __shared__ unsigned char msm[];
+    constexpr int TW = 64, TH = 8, N = KW * KH;
+    constexpr int rx = KW / 2, ry = KH / 2, sw = TW + KW - 1, shh = TH + KH - 1;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const long long fz = blockIdx.z;
+    const uint8_t *ps = s.p + fz * s.bstride;
+    for (int i = tid; i < sw * shh; i += 256) {
+        const int ty = i / sw, tx = i - ty * sw;
+        const int sx = min(max(x0 + tx - rx, 0), s.w - 1), sy = min(max(y0 + ty - ry, 0), s.h - 1);
+        const uint8_t *q = ps + (size_t)sy * s.pitch + (size_t)sx * BPP;
+#pragma unroll
+        for (int c = 0; c < BPP; c++) msm[(size_t)i * BPP + c] = q[c];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x * 2, ty = threadIdx.y;
+    if (x0 + tx >= d.w || y0 + ty >= d.h) return;
+    uint8_t *pd = d.p + fz * d.bstride + (size_t)(y0 + ty) * d.pitch + (size_t)(x0 + tx) * BPP;
+    const bool second = x0 + tx + 1 < d.w;
+#pragma unroll
+    for (int c = 0; c < BPP; c++) {
+        unsigned a[N];
+#pragma unroll
+        for (int j = 0; j < KH; j++) {
+            const uint8_t *row = msm + ((size_t)(ty + j) * sw + tx) * BPP + c;
+#pragma unroll
+            for (int i = 0; i < KW; i++) a[j * KW + i] = (unsigned)row[i * BPP] | ((unsigned)row[(i + 1) * BPP] << 16);
+        }
+        unsigned m;
+        if (N == 9) { MEDIAN_NET_9(a); m = a[MEDIAN_OUT_9]; }
+        else        { MEDIAN_NET_25(a); m = a[MEDIAN_OUT_25]; }
+        pd[c] = m & 0xFFu;
+        if (second) pd[BPP + c] = (m >> 16) & 0xFFu;
+    }
+}
+
 }  // namespace gmatb
 
 using namespace gmatb;
@@ -424,6 +475,15 @@ extern "C" int gmatb_median(const GmatbImage *src, const GmatbImage *dst, int kw
     PImg s, d;
     if (!to_pimg(src, &s) || !to_pimg(dst, &d) || !same_geom(s, d) || nbatch(src) != nbatch(dst)) return GMATB_ERR_INVAL;
     if (kw < 1 || kh < 1 || kw > 15 || kh > 15 || kw > s.w || kh > s.h) return GMATB_ERR_INVAL;
+    if ((kw == 3 && kh == 3) || (kw == 5 && kh == 5)) {
+        const size_t sm2 = (size_t)(64 + kw - 1) * (8 + kh - 1) * d.bpp;
+        dim3 b2(32, 8), g2((d.w + 63) / 64, (d.h + 7) / 8, nbatch(src));
+        cudaStream_t st = (cudaStream_t)stream;
+        if (kw == 3) { if (d.bpp == 3) median_net_kernel<3, 3, 3><<<g2, b2, sm2, st>>>(s, d); else median_net_kernel<4, 3, 3><<<g2, b2, sm2, st>>>(s, d); }
+        else         { if (d.bpp == 3) median_net_kernel<3, 5, 5><<<g2, b2, sm2, st>>>(s, d); else median_net_kernel<4, 5, 5><<<g2, b2, sm2, st>>>(s, d); }
+        count_launch();
+        return set_cuda_error(cudaGetLastError());
+    }
     const size_t smem = (size_t)(32 + kw - 1) * (8 + kh - 1) * d.bpp;
     dim3 b(32, 8), g((d.w + 31) / 32, (d.h + 7) / 8, nbatch(src));
     if (d.bpp == 3) median_kernel<3><<<g, b, smem, (cudaStream_t)stream>>>(s, d, kw, kh);
