@@ -222,7 +222,6 @@ def main():
     ms_step = ms / args.steps
     value = world * B * sw * sh / (ms_step * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    achieved = B * alg_bytes / (ms_step * 1e-3) / 1e9 * (launches / args.steps if launches else 1) / max(launches / args.steps, 1)
     # ---- secondary: default-parameter bicubic (A = 0: the 2-tap degenerate case at exactly 2:1) ----
     secondary = None
     if args.workload == "c2":
@@ -256,6 +255,9 @@ def main():
     e2e = {"value": world * Be * sw * sh * esteps / et / 1e9, "unit": "Gpx/s",
            "h2d_bytes_per_step": Be * sum(p[1] * p[2] for p in hs.planes), "d2h_bytes_per_step": Be * sum(p[1] * p[2] for p in hd.planes),
            "frames_per_step": Be, "steps": esteps}
+    if world > 1:
+        dist.barrier()                      # every rank reaches this point; rank 0 alone reports
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     traffic = None
@@ -281,8 +283,6 @@ def main():
             cb = {"value": None, "unit": "Gpx/s", "cores": 0, "kind": "port", "sample": "oracle/_ref not built"}
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
     return 0
 
 

@@ -486,11 +486,35 @@ extern "C" int gmatb_sws_scale(GmatbSws *c, const uint8_t *const src[4], const i
 }
 
 // HOST frames in, HOST frames out.  The device staging buffers mirror the host layout
-// byte for byte (same strides), so each direction is ONE async copy of the span.
+// byte for byte (same strides).  The batch is cut into chunks of frames that flow through
+// three streams -- copy-in, convert, copy-out -- linked by events, so that the PCIe uplink,
+// the kernels and the PCIe downlink overlap (the link is full duplex; the reference API has
+// no host-buffer call at all: its callers cudaMemcpy around sws_scale themselves).
+struct HostPipe {
+    cudaStream_t in, out;
+    cudaEvent_t ev_in[64], ev_k[64];
+    bool ok;
+};
+static HostPipe *host_pipe() {
+    static HostPipe hp;
+    static bool init = false;
+    if (!init) {
+        init = true;
+        hp.ok = cudaStreamCreateWithFlags(&hp.in, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&hp.out, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 64 && hp.ok; i++)
+            hp.ok = cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&hp.ev_k[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    return &hp;
+}
+
 extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, const GmatbImage *dst_host) {
     if (!c || !src_host || !dst_host) return GMATB_ERR_INVAL;
     GmatbImage s = *src_host, d = *dst_host;
     fix_nv12_uv(&s); fix_nv12_uv(&d);
+    const int n = s.batch > 1 ? s.batch : 1;
+    if ((d.batch > 1 ? d.batch : 1) != n) return GMATB_ERR_INVAL;
     uintptr_t slo, shi, dlo, dhi;
     image_span(&s, &slo, &shi); image_span(&d, &dlo, &dhi);
     if (shi <= slo || dhi <= dlo) return GMATB_ERR_INVAL;
@@ -504,11 +528,55 @@ extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, con
         if (s.data[p]) sdev.data[p] = ds + ((uintptr_t)s.data[p] - slo);
         if (d.data[p]) ddev.data[p] = dd + ((uintptr_t)d.data[p] - dlo);
     }
-    cudaError_t e = cudaMemcpyAsync(ds, (const void *)slo, shi - slo, cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) return set_cuda_error(e);
-    int rc = scale_batch(c, &sdev, &ddev);
+    HostPipe *hp = host_pipe();
+    // chunking needs frames that are whole, equally spaced byte ranges (the FrameBatch / frame-pool layout)
+    bool chunkable = hp->ok && n > 1;
+    const long long sfs = s.batch_stride[0], dfs = d.batch_stride[0];
+    for (int p = 0; p < 4 && chunkable; p++) {
+        if (s.data[p] && s.batch_stride[p] != sfs) chunkable = false;
+        if (d.data[p] && d.batch_stride[p] != dfs) chunkable = false;
+    }
+    if (chunkable && ((long long)(shi - slo) > sfs * n || (long long)(dhi - dlo) > dfs * n)) chunkable = false;
+    if (!chunkable) {
+        cudaError_t e = cudaMemcpyAsync(ds, (const void *)slo, shi - slo, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return set_cuda_error(e);
+        int rc = scale_batch(c, &sdev, &ddev);
+        if (rc) return rc;
+        e = cudaMemcpyAsync((void *)dlo, dd, dhi - dlo, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        return set_cuda_error(e);
+    }
+    int per = (n + 7) / 8;                       // ~8 chunks in flight
+    if (per < 1) per = 1;
+    const int nchunks = (n + per - 1) / per;
+    cudaError_t e = cudaSuccess;
+    int rc = 0;
+    for (int k = 0; k < nchunks && e == cudaSuccess && !rc; k++) {
+        const int f0 = k * per, fn = std::min(per, n - f0);
+        const size_t so = (size_t)f0 * sfs, sb = (f0 + fn == n) ? (shi - slo) - so : (size_t)fn * sfs;
+        const size_t dofs = (size_t)f0 * dfs, db = (f0 + fn == n) ? (dhi - dlo) - dofs : (size_t)fn * dfs;
+        e = cudaMemcpyAsync(ds + so, (const uint8_t *)slo + so, sb, cudaMemcpyHostToDevice, hp->in);
+        if (e == cudaSuccess) e = cudaEventRecord(hp->ev_in[k & 63], hp->in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, hp->ev_in[k & 63], 0);
+        if (e != cudaSuccess) break;
+        GmatbImage sc = sdev, dc = ddev;
+        sc.batch = fn; dc.batch = fn;
+        for (int p = 0; p < 4; p++) {
+            if (sc.data[p]) sc.data[p] = (uint8_t *)sc.data[p] + (size_t)f0 * s.batch_stride[p];
+            if (dc.data[p]) dc.data[p] = (uint8_t *)dc.data[p] + (size_t)f0 * d.batch_stride[p];
+        }
+        rc = scale_batch(c, &sc, &dc);
+        if (rc) break;
+        e = cudaEventRecord(hp->ev_k[k & 63], c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->out, hp->ev_k[k & 63], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t *)dlo + dofs, dd + dofs, db, cudaMemcpyDeviceToHost, hp->out);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(hp->in);
+    cudaError_t e3 = cudaStreamSynchronize(c->stream);
+    cudaError_t e4 = cudaStreamSynchronize(hp->out);
     if (rc) return rc;
-    e = cudaMemcpyAsync((void *)dlo, dd, dhi - dlo, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = e3;
+    if (e == cudaSuccess) e = e4;
     return set_cuda_error(e);
 }
