@@ -222,21 +222,26 @@ def main():
     ms_step = ms / args.steps
     value = world * B * sw * sh / (ms_step * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    # ---- secondary: default-parameter bicubic (A = 0: the 2-tap degenerate case at exactly 2:1) ----
+    # ---- secondary measurements on the same frames (reported beside the headline) ----------------
+    #  * default-parameter bicubic (A = 0: at exactly 2:1 the outer taps vanish)
+    #  * SWS_BILINEAR: what the reference really executes for EVERY flag (swscale_cuda.c:305 bug)
     secondary = None
     if args.workload == "c2":
-        c2 = SwsContext(sw, sh, sfmt, dw, dh, dfmt, flags, None)
-        for _ in range(3):
-            c2.scale(src, dst)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            c2.scale(src, dst)
-        a1.record(); torch.cuda.synchronize()
-        m2 = a0.elapsed_time(a1) / args.steps
-        secondary = {"workload": "same, default bicubic parameter (A=0)", "value": B * sw * sh / (m2 * 1e-3) / 1e9,
-                     "achieved_gbs": B * alg_bytes / (m2 * 1e-3) / 1e9, "frac": B * alg_bytes / (m2 * 1e-3) / 1e9 / peak}
+        secondary = []
+        for label, fl, par in (("default bicubic parameter (A=0)", SWS.BICUBIC, None),
+                               ("SWS_BILINEAR (the reference's actual resize, R-A arithmetic)", SWS.BILINEAR, None)):
+            c2 = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.HWACCEL_CUDA, par)
+            for _ in range(3):
+                c2.scale(src, dst)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                c2.scale(src, dst)
+            a1.record(); torch.cuda.synchronize()
+            m2 = a0.elapsed_time(a1) / args.steps
+            secondary.append({"workload": "same frames, " + label, "value": B * sw * sh / (m2 * 1e-3) / 1e9, "unit": "Gpx/s (this rank)",
+                              "achieved_gbs": B * alg_bytes / (m2 * 1e-3) / 1e9, "frac": B * alg_bytes / (m2 * 1e-3) / 1e9 / peak})
     # ---- e2e: host buffers in, host buffers out, through the public call --------------------------
     Be = min(B, 16)
     hs = FrameBatch(sfmt, sw, sh, Be, pinned=True); hs.buf.copy_(src.buf[:Be * src.frame_bytes].cpu())
@@ -263,7 +268,9 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+        tj = json.load(open(tp)).get(args.workload)
+        if tj:      # ncu dram bytes per frame of the dominant kernel, scaled to this launch's frame count
+            traffic = tj["per_frame"] * B
     line = {"metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 in/out, f32 arithmetic" if sname != "P010LE" else "u16 in/out, f32 arithmetic", "data": "synthetic",

@@ -188,7 +188,7 @@ __device__ __forceinline__ void store_rgb_px(uint8_t *p, int r, int g, int b) {
 // yuv -> packed rgb
 // ---------------------------------------------------------------------------
 template <int L, int SBITS, int DST, bool SPARSE>
-__global__ void __launch_bounds__(256) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
+__global__ void __launch_bounds__(256, 4) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (x0 >= src.w || y0 >= src.h) return;

@@ -11,6 +11,7 @@
 // -ffp-contract=off) performs the same IEEE operations in the same order.
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -219,6 +220,10 @@ __host__ __device__ inline int border_idx(int i, int n, int mode) {
     default: return -1;
     }
 }
+
+}  // namespace gmatb
+#include "gauss_stream.cuh"
+namespace gmatb {
 
 // ---------------------------------------------------------------------------
 // gaussian: separable, fp32.  t(y,x) = sum_i kx[i]*src(y, x+i-rx) accumulated left to
@@ -455,6 +460,31 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
     // OpenCV / CV-CUDA rule: sigmaY <= 0 takes sigmaX; a sigma <= 0 is derived from its kernel size
     gauss_weights(kw, sigma_x, G.kx);
     gauss_weights(kh, sigma_y > 0.0 ? sigma_y : sigma_x, G.ky);
+    if ((kw == 3 || kw == 5 || kw == 7) && (kh == 3 || kh == 5 || kh == 7) && s.w >= 4 + kw) {
+        GaussS S;
+        memset(&S, 0, sizeof(S));
+        for (int i = 0; i < kw; i++) S.kx[i] = G.kx[i];
+        for (int i = 0; i < kh; i++) S.ky[i] = G.ky[i];
+        S.border = border;
+        const int nb = nbatch(src);
+        const int wx = (d.w + 3) / 4;                 // threads per row
+        long long want = 148LL * 16 * 32 * 4;         // threads
+        int bands = (int)((want + (long long)wx * nb - 1) / ((long long)wx * nb));
+        bands = std::max(1, std::min(bands, (d.h + 31) / 32));
+        S.band = (d.h + bands - 1) / bands;
+        bands = (d.h + S.band - 1) / S.band;
+        dim3 g2((wx + 127) / 128, bands, nb);
+        cudaStream_t st = (cudaStream_t)stream;
+#define GS(B, KW_, KH_) gauss_stream_kernel<B, KW_, KH_><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.w, d.h, S)
+#define GK(B, KW_) do { if (kh == 3) GS(B, KW_, 3); else if (kh == 5) GS(B, KW_, 5); else GS(B, KW_, 7); } while (0)
+#define GB(B) do { if (kw == 3) GK(B, 3); else if (kw == 5) GK(B, 5); else GK(B, 7); } while (0)
+        if (d.bpp == 3) GB(3); else GB(4);
+#undef GS
+#undef GK
+#undef GB
+        count_launch();
+        return set_cuda_error(cudaGetLastError());
+    }
     const int sw = 32 + kw - 1, sh = 16 + kh - 1;
     const size_t smem = (((size_t)sh * sw * d.bpp + 15) & ~(size_t)15) + (size_t)sh * 32 * d.bpp * sizeof(float);
     dim3 b(32, 8), g((d.w + 31) / 32, (d.h + 15) / 16, nbatch(src));

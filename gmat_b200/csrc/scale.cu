@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "scale_fused.cuh"
+#include "scale_bilinear2.cuh"
 #include "scale_generic.cuh"
 
 namespace gmatb {
@@ -149,6 +150,10 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
         c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
         c->path = PATH_FUSED2;
     }
+    // bilinear at exactly 2:1 from 8-bit yuv: the integer fast path (scale_bilinear2.cuh)
+    if (c->kind == K_YUV2RGB && c->algo == RS_BILINEAR && sparse && srcW == 2 * dstW && srcH == 2 * dstH && (srcW % 8) == 0 &&
+        fmt_bits(srcFormat) == 8 && rgb_dst_code(dstFormat) <= D_BGRA)
+        c->path = PATH_FUSED2;
     return c;
 }
 
@@ -183,23 +188,13 @@ static NormK norm_k(int bits) {
     return k;
 }
 
-static int fused_minb() {      // tuning knob (resident warps per SM the register allocation must allow)
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("GMATB_FUSED_MINB"); v = e ? atoi(e) : 20; }
-    return v;
-}
-
+// MINB = resident warps per SM the register allocation must allow (__launch_bounds__(32, MINB)).
+// Measured on B200 (C2, A=-0.75): 16/20 -> 707 Gpx/s, 24/28/32 (spilling) -> 660.  20 it is.
 template <int L, int SBITS, int DST>
 static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused2Params &P) {
-#define K(T, W, M) fused_csc_scale2_kernel<L, SBITS, DST, T, W, M><<<g, 32, 0, st>>>(P)
-    if (wrap) { if (taps2) K(true, true, 16); else K(false, true, 16); return; }
-    if (L == L_NV12 && SBITS == 8 && DST == D_RGB24) {       // the headline instantiation carries the tuning variants
-        const int m = fused_minb();
-        if (taps2) { if (m >= 32) K(true, false, 32); else if (m >= 28) K(true, false, 28); else if (m >= 24) K(true, false, 24); else if (m >= 20) K(true, false, 20); else K(true, false, 16); }
-        else       { if (m >= 32) K(false, false, 32); else if (m >= 28) K(false, false, 28); else if (m >= 24) K(false, false, 24); else if (m >= 20) K(false, false, 20); else K(false, false, 16); }
-        return;
-    }
-    if (taps2) K(true, false, 16); else K(false, false, 16);
+#define K(T, W) fused_csc_scale2_kernel<L, SBITS, DST, T, W, 20><<<g, 32, 0, st>>>(P)
+    if (wrap) { if (taps2) K(true, true); else K(false, true); }
+    else      { if (taps2) K(true, false); else K(false, false); }
 #undef K
 }
 template <int L, int SBITS>
@@ -248,6 +243,21 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     const int bits = fmt_bits(src->format);
     const int dc = rgb_dst_code(dst->format);
     const bool semi = np == 2;
+    if (c->ra) {      // bilinear 2:1 integer kernel
+        if (!planes_aligned(P.src, np, 16) || !planes_aligned(P.dst, 1, (dc == D_RGB24 || dc == D_BGR24) ? 4 : 16)) return 0;
+        dim3 g((c->srcW + 255) / 256, (c->srcH / 2 + 7) / 8, src->batch > 1 ? src->batch : 1), b(32, 8);
+#define BL(Lx) do { switch (dc) { \
+            case D_RGB24: fused_csc_bilinear2_kernel<Lx, D_RGB24><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
+            case D_BGR24: fused_csc_bilinear2_kernel<Lx, D_BGR24><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
+            case D_RGBA:  fused_csc_bilinear2_kernel<Lx, D_RGBA><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
+            default:      fused_csc_bilinear2_kernel<Lx, D_BGRA><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; } } while (0)
+        if (semi) BL(L_NV12); else BL(L_I420);
+#undef BL
+        count_launch();
+        int rc0 = set_cuda_error(cudaGetLastError());
+        *done = (rc0 == 0);
+        return rc0;
+    }
     // vector-access preconditions; otherwise the generic kernel takes the frame
     if (!planes_aligned(P.src, 1, bits == 8 ? 8 : 16)) return 0;
     if (semi ? !planes_aligned(P.src, 2, bits == 8 ? 8 : 16) : !(planes_aligned(P.src, 3, bits == 8 ? 4 : 8))) return 0;

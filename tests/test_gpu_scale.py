@@ -49,6 +49,36 @@ def test_generic_any_ratio_vs_oracle(dev, name, flag, param, sw, sh, dw, dh):
         assert_same(dd, ref, f"{name}{param} {sfmt}->{dfmt} {sw}x{sh}->{dw}x{dh} path {c.path}")
 
 
+@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 48, 32, 24), (16, 4, 8, 2), (8, 2, 4, 1), (512, 130, 256, 65), (264, 64, 132, 32)])
+@pytest.mark.parametrize("sfmt,dfmt", [(FMT.NV12, FMT.RGB24), (FMT.YUV420P, FMT.BGRA), (FMT.NV12, FMT.BGR24), (FMT.YUV420P, FMT.RGBA)])
+def test_fused_bilinear_2to1_vs_oracle(dev, sw, sh, dw, dh, sfmt, dfmt):
+    """SWS_BILINEAR (what the reference always runs): integer fast path vs the R-A restatement"""
+    src = FrameBatch(sfmt, sw, sh, 2); src.fill_lcg(seed=sw + dh)
+    c = SwsContext(sw, sh, sfmt, dw, dh, dfmt, SWS.BILINEAR | HW)
+    assert c.path == 1
+    ds = src.to(dev); dd = FrameBatch(dfmt, dw, dh, 2, device=dev)
+    c.scale(ds, dd); torch.cuda.synchronize()
+    ref = FrameBatch(dfmt, dw, dh, 2); orc.yuv2rgb_scale(src, ref, tables(c), ra=1)
+    assert_same(dd, ref, f"bilinear {sfmt}->{dfmt} {sw}x{sh}->{dw}x{dh}")
+
+
+def test_fused_bilinear_4k_equals_generic(dev):
+    sw, sh, dw, dh = 3840, 2160, 1920, 1080
+    src = FrameBatch(FMT.NV12, sw, sh, 1, device=dev); host = src.fill_lcg(seed=78)
+    c = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.RGB24, SWS.BILINEAR | HW)
+    a = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev); c.scale(src, a)
+    odd = FrameBatch(FMT.NV12, sw, sh, 1, device=dev, align=1)
+    odd.planes = [(0, sw + 3, sh, sw), ((sw + 3) * sh, sw + 3, sh // 2, sw)]
+    odd.frame_bytes = (sw + 3) * (sh + sh // 2)
+    odd.buf = torch.zeros(odd.frame_bytes, dtype=torch.uint8, device=dev)
+    h2 = np.zeros(odd.frame_bytes, np.uint8)
+    for p in range(2):
+        odd.plane_view(h2, 0, p)[...] = src.plane_view(host, 0, p)
+    odd.upload(h2)
+    b = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev); c.scale(odd, b); torch.cuda.synchronize()
+    assert torch.equal(a.buf, b.buf)
+
+
 def test_device_filter_tables_vs_cpu_restatement(dev):
     """bicubic / bilinear / nearest tables are bit-exact on the CPU; Lanczos (GPU __sinf) within 2e-6"""
     for (s, d) in ((3840, 1920), (1920, 1281), (33, 50), (100, 12)):

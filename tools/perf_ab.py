@@ -24,7 +24,8 @@ def report(name, ms, px, nbytes):
 B = 64
 src = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); src.buf.random_(0, 256)
 dst = FrameBatch(FMT.RGB24, 1920, 1080, B, device=dev)
-for label, flag, param in (("bicubic A=-0.75", SWS.BICUBIC, (0.75,)), ("bicubic default (A=0)", SWS.BICUBIC, None), ("lanczos", SWS.LANCZOS, None)):
+for label, flag, param in (("bicubic A=-0.75", SWS.BICUBIC, (0.75,)), ("bicubic default (A=0)", SWS.BICUBIC, None), ("lanczos", SWS.LANCZOS, None),
+                           ("BILINEAR (reference's actual algo)", SWS.BILINEAR, None)):
     c = SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, flag | SWS.HWACCEL_CUDA, param)
     ms = timeit(lambda: c.scale(src, dst))
     report(f"C2 4K NV12->1080p RGB24 {label}", ms, B * 3840 * 2160, B * 18662400)
