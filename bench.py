@@ -33,7 +33,9 @@ WORKLOADS = {
     "c2_default": ("NV12", 3840, 2160, "RGB24", 1920, 1080, "BICUBIC", None),
     "c3":         ("P010LE", 7680, 4320, "RGB48LE", 3840, 2160, "LANCZOS", None),
     "csc":        ("NV12", 3840, 2160, "RGB24", 3840, 2160, "BICUBIC", None),
+    "c1":         ("NV12", 1920, 1080, "RGB24", 1920, 1080, "BICUBIC", None),     # BASELINE configs[0]
 }
+# BASELINE configs[3] / configs[4] (chain and mixed sizes) are measured by run_c4 / run_c5 below
 METRIC = "Gpixels/s 4K NV12->RGB24+bicubic->1080p; %HBM roofline; 1/2/4/8 GPU"
 
 
@@ -136,18 +138,91 @@ def cpu_reference(workload, budget_s=12.0, threads=None):
             "seconds": dt, "frames": frames}
 
 
+def run_extra(args):
+    """BASELINE configs[3] (C4: rotate 30 deg -> gaussian 5x5 -> scale to 1080p on 4K rgb24, every filter
+    materialising its frame like a filtergraph) and configs[4] (C5: equal thirds of 1080p / 4K / 8K NV12 ->
+    RGB24 at half size), frames sharded by batch index over the ranks.  Secondary benchmarks: same JSON shape."""
+    import torch
+    import torch.distributed as dist
+    import gmat_b200 as g
+    from gmat_b200 import BORDER, FMT, SWS, FrameBatch, SwsContext
+    from gmat_b200.dist import init
+    rank, world, local = init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peak, peak_src = measured_peak()
+    if args.workload == "c4":
+        B = max(1, 256 // 8 if world == 1 else 256 // world)          # batch 256 over 8 GPUs = 32 per GPU
+        a = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev); a.buf.random_(0, 256)
+        b = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev)
+        c = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev)
+        d = FrameBatch(FMT.RGB24, 1920, 1080, B, device=dev)
+        sc = SwsContext(3840, 2160, FMT.RGB24, 1920, 1080, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
+
+        def step():
+            g.rotate(a, b, 30.0, -282.7688, 1104.6926, "linear")
+            g.gaussian(b, c, 5, 5, 1.1, 1.1, BORDER.REFLECT101)
+            sc.scale(c, d)
+        px = B * 3840 * 2160
+        alg = B * 130636800
+        desc = "C4: 4K rgb24 rotate(30deg, linear) -> gaussian 5x5 sigma 1.1 reflect101 -> bicubic scale to 1080p, each stage materialised"
+    else:
+        n = max(1, args.batch // 3)
+        sizes = ((1920, 1080), (3840, 2160), (7680, 4320))
+        items = []
+        for (w, h) in sizes:
+            s_ = FrameBatch(FMT.NV12, w, h, n if w < 7680 else max(1, n // 2), device=dev); s_.buf.random_(0, 256)
+            d_ = FrameBatch(FMT.RGB24, w // 2, h // 2, s_.n, device=dev)
+            items.append((SwsContext(w, h, FMT.NV12, w // 2, h // 2, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA, (0.75,)), s_, d_))
+
+        def step():
+            for ctx, s_, d_ in items:
+                ctx.scale(s_, d_)
+        px = sum(s_.n * s_.w * s_.h for _, s_, _ in items)
+        alg = int(px * 2.25)
+        desc = "C5: mixed 1080p/4K/8K NV12 -> RGB24 at half size, bicubic R-B param0=0.75, " + "+".join(str(s_.n) for _, s_, _ in items) + " frames per GPU"
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = g.lib().gmatb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = g.lib().gmatb_launch_count() - l0
+    if world > 1:
+        tt = torch.tensor([ms], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = tt.item()
+        dist.barrier(); dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    ms_step = ms / args.steps
+    print(json.dumps({"metric": METRIC, "value": world * px / (ms_step * 1e-3) / 1e9, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u8 in/out, f32 arithmetic", "data": "synthetic", "config": {"workload": desc},
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": alg / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+                      "gpu_launches": int(launches)}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4", "c5"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload in ("c4", "c5"):
+        return run_extra(args)
     sname, sw, sh, dname, dw, dh, flag, param0 = WORKLOADS[args.workload]
     wl_desc = (f"{args.workload.upper()}: {sw}x{sh} {sname} -> {dw}x{dh} {dname}, "
                f"{flag.lower()} R-B" + (f" param0={param0}" if param0 is not None else " default param"))

@@ -19,7 +19,7 @@
 
 namespace gmatb {
 
-enum { L_NV12 = 0, L_I420 = 1 };   // chroma layout: semi-planar / planar
+enum { L_NV12 = 0, L_I420 = 1, L_RGB3 = 2 };   // source layout: semi-planar yuv / planar yuv / packed 3-byte rgb (fused scaler only)
 enum { D_RGB24 = 0, D_BGR24, D_RGBA, D_BGRA, D_RGB48, D_BGR48, D_RGBA64, D_BGRA64, D_COUNT };
 
 __host__ __device__ constexpr int dst_bpp(int d) {

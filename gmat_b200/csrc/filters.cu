@@ -123,8 +123,11 @@ __device__ __forceinline__ float cubic_w(float d) {   // Keys kernel, A = -0.75,
 
 template <int BPP>
 __global__ void __launch_bounds__(256) rotate_kernel(PImg s, PImg d, RotParams R) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
+    // a warp covers a 16x2 block of the destination (a compact source footprint: fewer cache lines per
+    // gather than a 32x1 row), the CTA 32x8
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
+    const int y = blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);
     if (x >= d.w || y >= d.h) return;
     const long long fz = blockIdx.z;
     const double dx = __dsub_rn((double)x, R.shx), dy = __dsub_rn((double)y, R.shy);
@@ -180,16 +183,43 @@ __global__ void __launch_bounds__(256) rotate_kernel(PImg s, PImg d, RotParams R
             const float ax = __fsub_rn((float)x2, sx), bx = __fsub_rn(sx, (float)x1);
             const float ay = __fsub_rn((float)y2, sy), by = __fsub_rn(sy, (float)y1);
             const float w00 = __fmul_rn(ax, ay), w01 = __fmul_rn(bx, ay), w10 = __fmul_rn(ax, by), w11 = __fmul_rn(bx, by);
-            const uint8_t *q00 = ps + (size_t)y1 * s.pitch + (size_t)x1 * BPP;
-            const uint8_t *q01 = ps + (size_t)y1 * s.pitch + (size_t)x2r * BPP;
-            const uint8_t *q10 = ps + (size_t)y2r * s.pitch + (size_t)x1 * BPP;
-            const uint8_t *q11 = ps + (size_t)y2r * s.pitch + (size_t)x2r * BPP;
+            // the two taps of a row are 2*BPP contiguous bytes: fetch them as aligned words + funnel shift
+            // instead of 2*BPP byte loads (the gather is LSU-bound)
+            float p00[BPP], p01[BPP], p10[BPP], p11[BPP];
+            const bool wordable = (((uintptr_t)ps | (uintptr_t)s.pitch) & 3) == 0;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const uint8_t *row = ps + (size_t)(rr ? y2r : y1) * s.pitch;
+                float (&pa)[BPP] = rr ? p10 : p00;
+                float (&pb)[BPP] = rr ? p11 : p01;
+                if (wordable && x2r == x2 && x1 >= 0) {
+                    const uintptr_t a = (uintptr_t)(row + (size_t)x1 * BPP);
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+                    const unsigned sh = (unsigned)(a & 3) * 8;
+                    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+                    const uint32_t w2 = (BPP == 4 || sh == 24) ? __ldg(q + 2) : 0u;       // bytes 6..7 of a 3-byte pair only when misaligned by 3
+                    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+                    // byte -> float through PRMT magic numbers (the I2F unit is 8x slower than the FP32 pipe)
+                    if (BPP == 3) {
+                        pa[0] = byte_magic<0>(v0) - GMATB_MAGIC; pa[1] = byte_magic<1>(v0) - GMATB_MAGIC; pa[2] = byte_magic<2>(v0) - GMATB_MAGIC;
+                        pb[0] = byte_magic<3>(v0) - GMATB_MAGIC; pb[1] = byte_magic<0>(v1) - GMATB_MAGIC; pb[2] = byte_magic<1>(v1) - GMATB_MAGIC;
+                    } else {
+                        pa[0] = byte_magic<0>(v0) - GMATB_MAGIC; pa[1] = byte_magic<1>(v0) - GMATB_MAGIC;
+                        pa[2] = byte_magic<2>(v0) - GMATB_MAGIC; pa[BPP - 1] = byte_magic<3>(v0) - GMATB_MAGIC;
+                        pb[0] = byte_magic<0>(v1) - GMATB_MAGIC; pb[1] = byte_magic<1>(v1) - GMATB_MAGIC;
+                        pb[2] = byte_magic<2>(v1) - GMATB_MAGIC; pb[BPP - 1] = byte_magic<3>(v1) - GMATB_MAGIC;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BPP; c++) { pa[c] = (float)row[(size_t)x1 * BPP + c]; pb[c] = (float)row[(size_t)x2r * BPP + c]; }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < BPP; c++) {
-                float a = __fmul_rn((float)q00[c], w00);
-                a = __fmaf_rn((float)q01[c], w01, a);
-                a = __fmaf_rn((float)q10[c], w10, a);
-                a = __fmaf_rn((float)q11[c], w11, a);
+                float a = __fmul_rn(p00[c], w00);
+                a = __fmaf_rn(p01[c], w01, a);
+                a = __fmaf_rn(p10[c], w10, a);
+                a = __fmaf_rn(p11[c], w11, a);
                 out[c] = min(max(__float2int_rn(a), 0), 255);
             }
         }

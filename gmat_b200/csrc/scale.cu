@@ -150,6 +150,17 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
         c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
         c->path = PATH_FUSED2;
     }
+    // packed 3-byte rgb -> same format at exactly 2:1: the fused kernel without its colour conversion
+    if (c->kind == K_RGB2RGB && !c->ra && (srcFormat == GMATB_FMT_RGB24 || srcFormat == GMATB_FMT_BGR24) &&
+        srcW == 2 * dstW && srcH == 2 * dstH && (srcW % 8) == 0) {
+        float4 hx, hy;
+        cudaMemcpy(&hx, c->cx[0], sizeof(hx), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&hy, c->cy[0], sizeof(hy), cudaMemcpyDeviceToHost);
+        c->wx[0] = hx.x; c->wx[1] = hx.y; c->wx[2] = hx.z; c->wx[3] = hx.w;
+        c->wy[0] = hy.x; c->wy[1] = hy.y; c->wy[2] = hy.z; c->wy[3] = hy.w;
+        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
+        c->path = PATH_FUSED2;
+    }
     // bilinear at exactly 2:1 from 8-bit yuv: the integer fast path (scale_bilinear2.cuh)
     if (c->kind == K_YUV2RGB && c->algo == RS_BILINEAR && sparse && srcW == 2 * dstW && srcH == 2 * dstH && (srcW % 8) == 0 &&
         fmt_bits(srcFormat) == 8 && rgb_dst_code(dstFormat) <= D_BGRA)
@@ -238,11 +249,12 @@ static bool planes_aligned(const Img &a, int np, int al) {
 static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
     *done = false;
     Fused2Params P;
-    const int np = fmt_planes(src->format);
+    const int np = is_yuv(src->format) ? fmt_planes(src->format) : 1;
     if (!to_img(src, &P.src, np) || !to_img(dst, &P.dst, 1)) return GMATB_ERR_INVAL;
     const int bits = fmt_bits(src->format);
     const int dc = rgb_dst_code(dst->format);
     const bool semi = np == 2;
+    const bool rgbsrc = c->kind == K_RGB2RGB;
     if (c->ra) {      // bilinear 2:1 integer kernel
         if (!planes_aligned(P.src, np, 16) || !planes_aligned(P.dst, 1, (dc == D_RGB24 || dc == D_BGR24) ? 4 : 16)) return 0;
         dim3 g((c->srcW + 255) / 256, (c->srcH / 2 + 7) / 8, src->batch > 1 ? src->batch : 1), b(32, 8);
@@ -260,7 +272,7 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     }
     // vector-access preconditions; otherwise the generic kernel takes the frame
     if (!planes_aligned(P.src, 1, bits == 8 ? 8 : 16)) return 0;
-    if (semi ? !planes_aligned(P.src, 2, bits == 8 ? 8 : 16) : !(planes_aligned(P.src, 3, bits == 8 ? 4 : 8))) return 0;
+    if (!rgbsrc && (semi ? !planes_aligned(P.src, 2, bits == 8 ? 8 : 16) : !(planes_aligned(P.src, 3, bits == 8 ? 4 : 8)))) return 0;
     const int dal = (dc == D_RGB24 || dc == D_BGR24) ? 4 : (dc == D_RGB48 || dc == D_BGR48) ? 8 : 16;
     if (!planes_aligned(P.dst, 1, dal)) return 0;
     P.M = c->M;
@@ -281,7 +293,12 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     dim3 g(warps_x, nb, batch);
     int rc;
     const bool wrap = P.wrap != 0;
-    if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
+    if (rgbsrc) {
+        // same component order in and out: run the RGB24 instantiation for both rgb24 and bgr24
+        launch_fused_t<L_RGB3, 8, D_RGB24>(c->taps2, wrap, g, c->stream, P);
+        count_launch();
+        rc = set_cuda_error(cudaGetLastError());
+    } else if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
     else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, wrap, g, c->stream, P);
     *done = (rc == 0);
     return rc;
@@ -430,6 +447,11 @@ static int scale_batch(GmatbSws *c, const GmatbImage *src_in, const GmatbImage *
         return run_generic(c, 0, s, d, c->dstW, c->dstH, np == 2 ? GS_NV12 : GS_I420, 3, bits, rgb_dst_code(dst.format), batch);
     }
     if (c->kind == K_RGB2RGB) {
+        if (c->path == PATH_FUSED2) {
+            bool done = false;
+            int rc = run_fused(c, &src, &dst, &done);
+            if (rc || done) return rc;
+        }
         return plane_resample(c, 0, &src, &dst, 0, c->srcW, c->srcH, c->dstW, c->dstH, rgb_channels(src.format), bits);
     }
     if (c->kind == K_RGB2YUV) {   // resize first, convert at destination size (swscale_cuda.c:312-341)

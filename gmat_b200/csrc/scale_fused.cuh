@@ -77,6 +77,40 @@ __device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, 
     }
 }
 
+// packed 3-byte rgb source (rgb24 -> rgb24 scaling: no colour conversion, same resample)
+struct RawRowRGB { uint2 t[3], b[3]; };
+__device__ __forceinline__ void fused_load_rgb(const Fused2Params &P, long long fz, int xs, int k, RawRowRGB &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)xs * 3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        R.t[i] = ldg64(py + (size_t)rt * P.src.pl[0].pitch + 8 * i);
+        R.b[i] = ldg64(py + (size_t)rb * P.src.pl[0].pitch + 8 * i);
+    }
+}
+template <int L, int SBITS> struct RowSel { typedef RawRow<SBITS> type; };
+template <> struct RowSel<L_RGB3, 8> { typedef RawRowRGB type; };
+template <int L> __device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRowRGB &R) {
+    fused_load_rgb(P, fz, xs, k, R);
+}
+// byte B (0..23) of a 24-byte row -> magic float
+template <int B> __device__ __forceinline__ float rgb_byte_magic(const uint2 (&w)[3]) {
+    const uint32_t word = (B & 4) ? w[B >> 3].y : w[B >> 3].x;
+    return byte_magic<B & 3>(word);
+}
+// normalised sample pair of integer-valued inputs that are already in range: p = RN(j/max), no clamp needed
+__device__ __forceinline__ f2 norm2_inrange(float mt, float mb, const NormK &k) {
+    const f2 j = add2(pk(mt, mb), bc(-GMATB_MAGIC));
+    const f2 t = mul2(j, bc(k.klo));
+    return fma2(j, bc(k.khi), t);
+}
+template <int C> __device__ __forceinline__ void rgb_column(const RawRowRGB &R, const NormK &nk, f2 (&out)[3]) {
+    out[0] = norm2_inrange(rgb_byte_magic<3 * C>(R.t), rgb_byte_magic<3 * C>(R.b), nk);
+    out[1] = norm2_inrange(rgb_byte_magic<3 * C + 1>(R.t), rgb_byte_magic<3 * C + 1>(R.b), nk);
+    out[2] = norm2_inrange(rgb_byte_magic<3 * C + 2>(R.t), rgb_byte_magic<3 * C + 2>(R.b), nk);
+}
+
 // unpack the raw words into magic floats: ym[row][col], um/vm[chroma sample]
 template <int L>
 __device__ __forceinline__ void fused_unpack(const RawRow<8> &R, float (&yt)[8], float (&yb)[8], float (&um)[4], float (&vm)[4]) {
@@ -128,6 +162,27 @@ __device__ __forceinline__ f2 hpass(const float (&w)[4], f2 p0, f2 p1, f2 p2, f2
     return t;
 }
 
+// the 8 (top,bottom) column pairs of one iteration as normalised samples
+template <int L, int SBITS, bool SPARSE, typename Row>
+__device__ __forceinline__ void fused_produce(const Row &cur, const Fused2Params &P, f2 (&C)[8][3]) {
+    constexpr float CB = -(GMATB_MAGIC + (SBITS == 8 ? 128.f : 32768.f));
+    float yt[8], yb[8], um[4], vm[4];
+    fused_unpack<L>(cur, yt, yb, um, vm);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float fu, fv;
+        upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+        ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
+        fused_column<SBITS, SPARSE>(yt[2 * j], yb[2 * j], t, P, C[2 * j]);
+        fused_column<SBITS, SPARSE>(yt[2 * j + 1], yb[2 * j + 1], t, P, C[2 * j + 1]);
+    }
+}
+template <int L, int SBITS, bool SPARSE>
+__device__ __forceinline__ void fused_produce(const RawRowRGB &cur, const Fused2Params &P, f2 (&C)[8][3]) {
+    rgb_column<0>(cur, P.nk, C[0]); rgb_column<1>(cur, P.nk, C[1]); rgb_column<2>(cur, P.nk, C[2]); rgb_column<3>(cur, P.nk, C[3]);
+    rgb_column<4>(cur, P.nk, C[4]); rgb_column<5>(cur, P.nk, C[5]); rgb_column<6>(cur, P.nk, C[6]); rgb_column<7>(cur, P.nk, C[7]);
+}
+
 // DST: D_* code from csc.cu (packed rgb).  TAPS2: the outer weights of both axes are
 // exactly zero (default bicubic, A = 0, at 2:1), FFMA(0, p, t) == t is skipped.
 template <int L, int SBITS, int DST, bool TAPS2, bool WRAP, int MINB>
@@ -166,7 +221,7 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
         alpha_i = trunc_i(__fmul_rn(av, P.factor));
     }
 
-    RawRow<SBITS> cur, nxt;
+    typename RowSel<L, SBITS>::type cur, nxt;
     fused_load<L>(P, fz, xs, yo_begin - 1, cur);
 
 #pragma unroll 2
@@ -174,7 +229,15 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
         if (k < yo_end) fused_load<L>(P, fz, xs, k + 1, nxt);
         // ---- extra (halo) column for the warp's outer lanes ------------------------
         f2 E[3] = {0ull, 0ull, 0ull};
-        if (!TAPS2 && need_extra) {
+        if (!TAPS2 && need_extra && L == L_RGB3) {
+            const int H = P.src.h;
+            const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+            const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)xe * 3;
+            const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch, *qb = py + (size_t)rb * P.src.pl[0].pitch;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                E[c] = norm2_inrange(__uint_as_float(0x4B000000u | qa[c]), __uint_as_float(0x4B000000u | qb[c]), P.nk);
+        } else if (!TAPS2 && need_extra) {
             const int H = P.src.h;
             const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
             const int rc = min(max(k, 0), (H >> 1) - 1);
@@ -200,17 +263,8 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
             fused_column<SBITS, SPARSE>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, E);
         }
         // ---- colour conversion of the 8x2 block ------------------------------------
-        float yt[8], yb[8], um[4], vm[4];
-        fused_unpack<L>(cur, yt, yb, um, vm);
         f2 C[8][3];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float fu, fv;
-            upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-            ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
-            fused_column<SBITS, SPARSE>(yt[2 * j], yb[2 * j], t, P, C[2 * j]);
-            fused_column<SBITS, SPARSE>(yt[2 * j + 1], yb[2 * j + 1], t, P, C[2 * j + 1]);
-        }
+        fused_produce<L, SBITS, SPARSE>(cur, P, C);
         // ---- halo columns ------------------------------------------------------------
         f2 PL[3] = {0ull, 0ull, 0ull}, PR[3] = {0ull, 0ull, 0ull};
         if (!TAPS2) {

@@ -79,6 +79,41 @@ def test_fused_bilinear_4k_equals_generic(dev):
     assert torch.equal(a.buf, b.buf)
 
 
+@pytest.mark.parametrize("name,flag,param", ALGOS)
+@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 48, 32, 24), (16, 4, 8, 2), (8, 2, 4, 1), (512, 130, 256, 65)])
+def test_fused_rgb24_2to1_vs_oracle(dev, name, flag, param, sw, sh, dw, dh):
+    """rgb24 -> rgb24 at 2:1 runs the fused kernel without its colour conversion"""
+    for fmt in (FMT.RGB24, FMT.BGR24):
+        src = FrameBatch(fmt, sw, sh, 2); src.fill_lcg(seed=sw + dh)
+        c = SwsContext(sw, sh, fmt, dw, dh, fmt, flag | HW, param)
+        assert c.path == 1
+        ds = src.to(dev); dd = FrameBatch(fmt, dw, dh, 2, device=dev)
+        c.scale(ds, dd); torch.cuda.synchronize()
+        (cx, px), (cy, py) = tables(c)
+        ref = FrameBatch(fmt, dw, dh, 2)
+        for f in range(2):
+            s, d = src.image(f, 1), ref.image(f, 1)
+            orc.orc().orc_resample_packed(s.data[0], s.linesize[0], sw, sh, d.data[0], d.linesize[0], dw, dh, 3, 0,
+                                          orc.fptr(cx), orc.iptr(px), orc.fptr(cy), orc.iptr(py), 0, 0)
+        assert_same(dd, ref, f"rgb {name}{param} {sw}x{sh}->{dw}x{dh}")
+
+
+def test_fused_rgb24_4k_equals_generic(dev):
+    sw, sh, dw, dh = 3840, 2160, 1920, 1080
+    src = FrameBatch(FMT.RGB24, sw, sh, 1, device=dev); host = src.fill_lcg(seed=79)
+    c = SwsContext(sw, sh, FMT.RGB24, dw, dh, FMT.RGB24, SWS.BICUBIC | HW, (0.75,))
+    a = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev); c.scale(src, a)
+    odd = FrameBatch(FMT.RGB24, sw, sh, 1, device=dev, align=1)
+    odd.planes = [(0, sw * 3 + 5, sh, sw * 3)]
+    odd.frame_bytes = (sw * 3 + 5) * sh
+    odd.buf = torch.zeros(odd.frame_bytes, dtype=torch.uint8, device=dev)
+    h2 = np.zeros(odd.frame_bytes, np.uint8)
+    odd.plane_view(h2, 0, 0)[...] = src.plane_view(host, 0, 0)
+    odd.upload(h2)
+    b = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev); c.scale(odd, b); torch.cuda.synchronize()
+    assert torch.equal(a.buf, b.buf)
+
+
 def test_device_filter_tables_vs_cpu_restatement(dev):
     """bicubic / bilinear / nearest tables are bit-exact on the CPU; Lanczos (GPU __sinf) within 2e-6"""
     for (s, d) in ((3840, 1920), (1920, 1281), (33, 50), (100, 12)):
