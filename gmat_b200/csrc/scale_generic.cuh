@@ -51,14 +51,18 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
     const int W = P.src.w, H = P.src.h;
 
     // ---- stage A ------------------------------------------------------------------
-    for (int i = tid; i < ww * wh; i += blockDim.x) {
-        const int wy = i / ww, wx = i - wy * ww;
+    const int tx = tid & 31, tyy = tid >> 5;                 // 32 x 8 threads: no integer division in the loops
+    for (int wy = tyy; wy < wh; wy += 8)
+    for (int wx = tx; wx < ww; wx += 32) {
+        const int i = wy * ww + wx;
         const int sx = min(max(wx0 + wx, 0), W - 1), sy = min(max(wy0 + wy, 0), H - 1);
         float *o = Pw + (size_t)i * CH;
         if (P.src_kind == GS_PACKED) {
             const uint8_t *q = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)sy * P.src.pl[0].pitch + (size_t)sx * CH * SB;
             for (int c = 0; c < CH; c++) {
-                float j = SBITS == 8 ? (float)q[c] : (float)reinterpret_cast<const uint16_t *>(q)[c];
+                // int -> float through the 2^23 magic number (exact; the I2F unit is 8x slower than the FP32 pipe)
+                const unsigned jv = SBITS == 8 ? (unsigned)q[c] : (unsigned)reinterpret_cast<const uint16_t *>(q)[c];
+                const float j = __uint_as_float(0x4B000000u | jv) - GMATB_MAGIC;
                 o[c] = RA ? j : fma_sat(j, P.nk.khi, __fmul_rn(j, P.nk.klo));
             }
         } else {
@@ -77,7 +81,9 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
                 else { u = *reinterpret_cast<const uint16_t *>(qu); v = *reinterpret_cast<const uint16_t *>(qv); }
             }
             const float low = SBITS == 8 ? 16.f : 4096.f, mid = SBITS == 8 ? 128.f : 32768.f;
-            const float fy = (float)(int)y - low, fu = (float)(int)u - mid, fv = (float)(int)v - mid;
+            const float fy = __uint_as_float(0x4B000000u | y) - (GMATB_MAGIC + low);
+            const float fu = __uint_as_float(0x4B000000u | u) - (GMATB_MAGIC + mid);
+            const float fv = __uint_as_float(0x4B000000u | v) - (GMATB_MAGIC + mid);
             // scalar form of csc_pair_f (same IEEE operations)
             const float *m = P.M.m;
             float r, g, b;
@@ -100,8 +106,8 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
     }
     __syncthreads();
     // ---- stage B: horizontal ------------------------------------------------------
-    for (int i = tid; i < wh * tw; i += blockDim.x) {
-        const int wy = i / tw, xo = i - wy * tw;
+    for (int wy = tyy; wy < wh; wy += 8)
+    for (int xo = tx; xo < tw; xo += 32) {
         const float4 w = P.cx[xo0 + xo];
         const float *p = Pw + ((size_t)wy * ww + (P.px[xo0 + xo] - wx0)) * CH;
         float *h = Hs + ((size_t)wy * P.tile_w + xo) * CH;
@@ -117,8 +123,8 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
     // ---- stage C: vertical + store ------------------------------------------------
     const int out_ch = P.src_kind == GS_PACKED ? CH : dst_bpp(P.dst_code) / (dst_is16(P.dst_code) ? 2 : 1);
     const int smax = SBITS == 8 ? 255 : 65535;
-    for (int i = tid; i < th * tw; i += blockDim.x) {
-        const int ty = i / tw, xo = i - ty * tw;
+    for (int ty = tyy; ty < th; ty += 8)
+    for (int xo = tx; xo < tw; xo += 32) {
         const float4 w = P.cy[yo0 + ty];
         const float *h = Hs + ((size_t)(P.py[yo0 + ty] - wy0) * P.tile_w + xo) * CH;
         const size_t rs = (size_t)P.tile_w * CH;

@@ -29,6 +29,10 @@ for label, flag, param in (("bicubic A=-0.75", SWS.BICUBIC, (0.75,)), ("bicubic 
     c = SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, flag | SWS.HWACCEL_CUDA, param)
     ms = timeit(lambda: c.scale(src, dst))
     report(f"C2 4K NV12->1080p RGB24 {label}", ms, B * 3840 * 2160, B * 18662400)
+g720 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
+cg = SwsContext(3840, 2160, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
+report("generic: 4K NV12->720p RGB24 bicubic (3:1)", timeit(lambda: cg.scale(src, g720), 3), B * 3840 * 2160, B * (12441600 + 2764800))
+del g720
 d4 = FrameBatch(FMT.RGBA, 1920, 1080, B, device=dev)
 c = SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGBA, SWS.BICUBIC | SWS.HWACCEL_CUDA, (0.75,))
 report("C2 -> RGBA bicubic A=-0.75", timeit(lambda: c.scale(src, d4)), B * 3840 * 2160, B * (12441600 + 8294400))
