@@ -98,13 +98,20 @@ __global__ void filter_table_kernel(int algo, int src_n, int dst_n, float A, flo
 // Quantise-and-normalise one CSC result: r (float, unclamped) -> the sample the
 // reference's resize stage reads back from its u8/u16 intermediate image through the
 // texture unit, p = RN(clamp(trunc(r), 0, max) / max).
-//   m  = FADD.RZ(r, 2^23)           = 2^23 + trunc(r)     (r >= 0; r < 0 gives m < 2^23)
-//   j  = m - 2^23                   exact
-//   p  = sat(FFMA(j, khi, RN(j*klo)))   with khi + klo = 1/max to 48 bits
-// RN(j * RN(1/255)) != RN(j/255) for about half of all j, hence the two-term quotient;
-// it equals the correctly rounded quotient for every j in range (exhaustive check in
-// tests/test_oracle.py), the saturation implements both clamps (j < 0 -> 0, j > max -> 1).
-struct NormK { float khi, klo; };
+//   m  = FADD.RZ(r, 2^23)            = 2^23 + trunc(r)    (r >= 0; r < 0 gives m < 2^23)
+//   hi = FFMA(m, c1, -2^23*c1)       = j*c1 EXACTLY, j = m - 2^23:
+//          8 bit: c1 = 0x010101 * 2^-24, j*0x010101 < 2^24 is representable
+//         16 bit: c1 = 2^-16
+//   p  = sat(FFMA(hi, c2, hi))       c2 = 2^-24 (8 bit) or 2^-16 + 2^-32 (16 bit)
+// because 1/255 = 0x010101*2^-24 * (1 + 2^-24 + 2^-48 + ...) and 1/65535 =
+// 2^-16 * (1 + 2^-16 + 2^-32 + ...): the neglected tail is 2^-48 relative, far inside
+// the distance of any j/max from a rounding boundary (>= 2^-33 / 2^-41 relative), so
+// the single rounding of the last FFMA gives the correctly rounded quotient for every
+// j in range (exhaustive check in tests/test_oracle.py).  RN(j * RN(1/255)) alone is
+// wrong for about half of all j.  The saturation implements both clamps (j < 0 -> 0,
+// j > max -> 1).  The generic kernel keeps the older two-term form sat(FFMA(j, khi,
+// RN(j*klo))), khi + klo = 1/max to 48 bits (same exhaustive check).
+struct NormK { float khi, klo, c1, c0, c2; };
 
 __device__ __forceinline__ f2 add2_rz(f2 a, f2 b) {
     f2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
@@ -115,11 +122,10 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
 // two values at a time (packed where the ISA allows; .sat exists only on scalar ops)
 __device__ __forceinline__ f2 quant_norm2(f2 r, const NormK &k) {
     const f2 m = add2_rz(r, bc(GMATB_MAGIC));
-    const f2 j = add2(m, bc(-GMATB_MAGIC));
-    const f2 t = mul2(j, bc(k.klo));          // feeds an fma addend: ptxas cannot contract it further
-    float j0, j1, t0, t1;
-    upk(j, j0, j1); upk(t, t0, t1);
-    return pk(fma_sat(j0, k.khi, t0), fma_sat(j1, k.khi, t1));
+    const f2 hi = fma2(m, bc(k.c1), bc(k.c0));
+    float h0, h1;
+    upk(hi, h0, h1);
+    return pk(fma_sat(h0, k.c2, h0), fma_sat(h1, k.c2, h1));
 }
 
 }  // namespace gmatb

@@ -196,6 +196,10 @@ static NormK norm_k(int bits) {
     NormK k;
     k.khi = (float)inv;
     k.klo = (float)(inv - (double)k.khi);
+    // geometric-series form (resample_core.cuh): 1/255 = 0x010101 * 2^-24 * (1 + 2^-24 + ...)
+    k.c1 = bits == 8 ? 65793.0f / 16777216.0f : 1.0f / 65536.0f;
+    k.c0 = -8388608.0f * k.c1;
+    k.c2 = bits == 8 ? 1.0f / 16777216.0f : 1.0f / 65536.0f + 1.0f / 4294967296.0f;
     return k;
 }
 

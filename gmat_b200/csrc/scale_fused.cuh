@@ -101,9 +101,8 @@ template <int B> __device__ __forceinline__ float rgb_byte_magic(const uint2 (&w
 }
 // normalised sample pair of integer-valued inputs that are already in range: p = RN(j/max), no clamp needed
 __device__ __forceinline__ f2 norm2_inrange(float mt, float mb, const NormK &k) {
-    const f2 j = add2(pk(mt, mb), bc(-GMATB_MAGIC));
-    const f2 t = mul2(j, bc(k.klo));
-    return fma2(j, bc(k.khi), t);
+    const f2 hi = fma2(pk(mt, mb), bc(k.c1), bc(k.c0));
+    return fma2(hi, bc(k.c2), hi);
 }
 template <int C> __device__ __forceinline__ void rgb_column(const RawRowRGB &R, const NormK &nk, f2 (&out)[3]) {
     out[0] = norm2_inrange(rgb_byte_magic<3 * C>(R.t), rgb_byte_magic<3 * C>(R.b), nk);
@@ -148,6 +147,43 @@ __device__ __forceinline__ void fused_column(float ytm, float ybm, const ChromaT
     f2 r, g, b;
     csc_pair_f<SPARSE, SBITS == 16>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
     out[0] = quant_norm2(r, P.nk); out[1] = quant_norm2(g, P.nk); out[2] = quant_norm2(b, P.nk);
+}
+
+// raw samples of the one halo column a warp's outer lanes fetch themselves (prefetched one
+// iteration ahead like the strip itself: the consumer must not wait on an L2 round trip).
+//   8-bit yuv : w0 = top luma | bottom luma << 8 | U << 16 | V << 24
+//   16-bit yuv: w0 = top luma | bottom luma << 16, w1 = U | V << 16
+//   rgb       : w0 / w1 = the 3 bytes of the top / bottom pixel
+struct ExtraRaw { uint32_t w0, w1; };
+template <int L, int SBITS>
+__device__ __forceinline__ void extra_load(const Fused2Params &P, long long fz, int xe, int k, ExtraRaw &X) {
+    constexpr int SB = SBITS / 8;
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+    if (L == L_RGB3) {
+        const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch + (size_t)xe * 3;
+        const uint8_t *qb = py + (size_t)rb * P.src.pl[0].pitch + (size_t)xe * 3;
+        X.w0 = qa[0] | (qa[1] << 8) | (qa[2] << 16);
+        X.w1 = qb[0] | (qb[1] << 8) | (qb[2] << 16);
+        return;
+    }
+    const int rc = min(max(k, 0), (H >> 1) - 1);
+    const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch + xe * SB;
+    const uint8_t *qb = py + (size_t)rb * P.src.pl[0].pitch + xe * SB;
+    uint32_t a, b, u, v;
+    if (SBITS == 8) { a = *qa; b = *qb; }
+    else { a = *reinterpret_cast<const uint16_t *>(qa); b = *reinterpret_cast<const uint16_t *>(qb); }
+    if (L == L_NV12) {
+        const uint8_t *qc = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * 2 * SB;
+        if (SBITS == 8) { X.w0 = a | (b << 8) | ((uint32_t)*reinterpret_cast<const uint16_t *>(qc) << 16); X.w1 = 0; }
+        else { X.w0 = a | (b << 16); X.w1 = *reinterpret_cast<const uint32_t *>(qc); }
+    } else {
+        const uint8_t *qu = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * SB;
+        const uint8_t *qv = P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + (xe >> 1) * SB;
+        if (SBITS == 8) { u = *qu; v = *qv; X.w0 = a | (b << 8) | (u << 16) | (v << 24); X.w1 = 0; }
+        else { u = *reinterpret_cast<const uint16_t *>(qu); v = *reinterpret_cast<const uint16_t *>(qv); X.w0 = a | (b << 16); X.w1 = u | (v << 16); }
+    }
 }
 
 __device__ __forceinline__ f2 shfl_up2(f2 v) { return __shfl_up_sync(0xffffffffu, v, 1); }
@@ -223,44 +259,32 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
 
     typename RowSel<L, SBITS>::type cur, nxt;
     fused_load<L>(P, fz, xs, yo_begin - 1, cur);
+    ExtraRaw ecur = {0, 0}, enxt = {0, 0};
+    if (!TAPS2 && need_extra) extra_load<L, SBITS>(P, fz, xe, yo_begin - 1, ecur);
 
 #pragma unroll 2
     for (int k = yo_begin - 1; k <= yo_end; k++) {
-        if (k < yo_end) fused_load<L>(P, fz, xs, k + 1, nxt);
+        if (k < yo_end) {
+            fused_load<L>(P, fz, xs, k + 1, nxt);
+            if (!TAPS2 && need_extra) extra_load<L, SBITS>(P, fz, xe, k + 1, enxt);
+        }
         // ---- extra (halo) column for the warp's outer lanes ------------------------
         f2 E[3] = {0ull, 0ull, 0ull};
         if (!TAPS2 && need_extra && L == L_RGB3) {
-            const int H = P.src.h;
-            const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
-            const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)xe * 3;
-            const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch, *qb = py + (size_t)rb * P.src.pl[0].pitch;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                E[c] = norm2_inrange(__uint_as_float(0x4B000000u | qa[c]), __uint_as_float(0x4B000000u | qb[c]), P.nk);
+            E[0] = norm2_inrange(byte_magic<0>(ecur.w0), byte_magic<0>(ecur.w1), P.nk);
+            E[1] = norm2_inrange(byte_magic<1>(ecur.w0), byte_magic<1>(ecur.w1), P.nk);
+            E[2] = norm2_inrange(byte_magic<2>(ecur.w0), byte_magic<2>(ecur.w1), P.nk);
         } else if (!TAPS2 && need_extra) {
-            const int H = P.src.h;
-            const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
-            const int rc = min(max(k, 0), (H >> 1) - 1);
-            const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
-            unsigned a, b, u, v;
-            const uint8_t *qa = py + (size_t)rt * P.src.pl[0].pitch + xe * SB;
-            const uint8_t *qb = py + (size_t)rb * P.src.pl[0].pitch + xe * SB;
-            if (SBITS == 8) { a = *qa; b = *qb; }
-            else { a = *reinterpret_cast<const uint16_t *>(qa); b = *reinterpret_cast<const uint16_t *>(qb); }
-            if (L == L_NV12) {
-                const uint8_t *qc = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * 2 * SB;
-                if (SBITS == 8) { u = qc[0]; v = qc[1]; }
-                else { u = reinterpret_cast<const uint16_t *>(qc)[0]; v = reinterpret_cast<const uint16_t *>(qc)[1]; }
+            float fu, fv, ya, yb;
+            if (SBITS == 8) {
+                ya = byte_magic<0>(ecur.w0); yb = byte_magic<1>(ecur.w0);
+                upk(add2(pk(byte_magic<2>(ecur.w0), byte_magic<3>(ecur.w0)), bc(CB)), fu, fv);
             } else {
-                const uint8_t *qu = P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xe >> 1) * SB;
-                const uint8_t *qv = P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + (xe >> 1) * SB;
-                if (SBITS == 8) { u = *qu; v = *qv; }
-                else { u = *reinterpret_cast<const uint16_t *>(qu); v = *reinterpret_cast<const uint16_t *>(qv); }
+                ya = half_magic<0>(ecur.w0); yb = half_magic<1>(ecur.w0);
+                upk(add2(pk(half_magic<0>(ecur.w1), half_magic<1>(ecur.w1)), bc(CB)), fu, fv);
             }
-            float fu, fv;
-            upk(add2(pk(__uint_as_float(0x4B000000u | u), __uint_as_float(0x4B000000u | v)), bc(CB)), fu, fv);
             ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
-            fused_column<SBITS, SPARSE>(__uint_as_float(0x4B000000u | a), __uint_as_float(0x4B000000u | b), t, P, E);
+            fused_column<SBITS, SPARSE>(ya, yb, t, P, E);
         }
         // ---- colour conversion of the 8x2 block ------------------------------------
         f2 C[8][3];
@@ -332,6 +356,7 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
                 hb_prev[xo][c] = hbm[xo][c];
             }
         cur = nxt;
+        ecur = enxt;
     }
 }
 

@@ -75,6 +75,22 @@ def test_norm_two_term_is_exact():
     assert orc.orc().orc_check_norm(1) == 0
 
 
+def test_norm_geometric_form_is_exact():
+    """sat(FFMA(hi, c2, hi)), hi = j*c1 exactly, == RN(j/max) for every sample value: the form the
+    fused kernel uses (resample_core.cuh quant_norm2).  hi*(1+c2) has <= 48 significant bits, so the
+    float64 product-sum is exact and its cast to float32 is the FFMA's single rounding."""
+    for maxv, c1, c2 in ((255, 65793.0 / 2 ** 24, 2.0 ** -24), (65535, 2.0 ** -16, 2.0 ** -16 + 2.0 ** -32)):
+        j = np.arange(maxv + 1, dtype=np.float64)
+        assert np.float32(c1) == c1 and np.float32(c2) == c2
+        hi = j * c1
+        assert np.all(hi.astype(np.float32).astype(np.float64) == hi)           # representable: FFMA(m, c1, -2^23 c1) is exact
+        m = 8388608.0 + j
+        assert np.all((m * c1 - 8388608.0 * c1) == hi)
+        p = (hi * c2 + hi).astype(np.float32)
+        ref = j.astype(np.float32) / np.float32(maxv)                           # IEEE division: correctly rounded
+        assert np.array_equal(p, ref)
+
+
 def test_bicubic_coefficients_closed_form():
     # exact 2:1: fx = 0.5 for every output; A = -0.75 gives dyadic weights, default A = 0 a 2x2 box
     co, po = orc.filter_table(orc.ALGO["bicubic"], 3840, 1920, -0.75)
