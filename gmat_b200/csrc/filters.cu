@@ -84,22 +84,49 @@ __global__ void __launch_bounds__(256) flip_rows_kernel(PImg s, PImg d, int vec)
     else { const int n = min(16, rowb - b0); for (int i = 0; i < n; i++) pd[i] = ps[i]; }
 }
 
-template <int BPP>
+// mirror of 4 packed 3-byte pixels (12 bytes, words a0 a1 a2): p3 p2 p1 p0, 4 PRMTs
+__device__ __forceinline__ void mirror4_rgb(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
+    o0 = __byte_perm(a2, a1, 0x6321);                           // a9 a10 a11 a6
+    o1 = __byte_perm(__byte_perm(a1, a2, 0x0043), a0, 0x3710);  // a7 a8 a3 a4
+    o2 = __byte_perm(a1, a0, 0x6541);                           // a5 a0 a1 a2
+}
+
+// vec: 2 = 16 pixels per thread through 128-bit loads/stores (3-byte pixels: width % 16 == 0),
+//      1 = 4 pixels per thread through 32-bit words (3-byte pixels, width % 4 == 0) / one 128-bit word (4-byte pixels),
+//      0 = bytes.  PX = pixels per thread.
+template <int BPP, int PX>
 __global__ void __launch_bounds__(256) flip_cols_kernel(PImg s, PImg d, int also_rows, int vec) {
-    // 4 destination pixels per thread
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * PX;
     if (y >= d.h || x0 >= d.w) return;
     const long long fz = blockIdx.z;
     const int sy = also_rows ? s.h - 1 - y : y;
     const uint8_t *srow = s.p + fz * s.bstride + (size_t)sy * s.pitch;
     uint8_t *pd = d.p + fz * d.bstride + (size_t)y * d.pitch + (size_t)x0 * BPP;
+    if (BPP == 3 && PX == 16) {          // host guarantees width % 16 == 0 and 16-byte aligned rows
+        const uint8_t *q = srow + (size_t)(s.w - 16 - x0) * 3;
+        const uint4 A = ldg128(q), B = ldg128(q + 16), Cw = ldg128(q + 32);
+        uint4 o0, o1, o2;
+        mirror4_rgb(Cw.y, Cw.z, Cw.w, o0.x, o0.y, o0.z);
+        mirror4_rgb(B.z, B.w, Cw.x, o0.w, o1.x, o1.y);
+        mirror4_rgb(A.w, B.x, B.y, o1.z, o1.w, o2.x);
+        mirror4_rgb(A.x, A.y, A.z, o2.y, o2.z, o2.w);
+        stg128(pd, o0); stg128(pd + 16, o1); stg128(pd + 32, o2);
+        return;
+    }
+    if (BPP == 3 && vec && x0 + 4 <= d.w) {
+        const uint8_t *q = srow + (size_t)(s.w - 4 - x0) * 3;
+        uint32_t o0, o1, o2;
+        mirror4_rgb(ldg32(q), ldg32(q + 4), ldg32(q + 8), o0, o1, o2);
+        stg32(pd, o0); stg32(pd + 4, o1); stg32(pd + 8, o2);
+        return;
+    }
     if (BPP == 4 && vec && x0 + 4 <= d.w) {
         uint4 v = ldg128(srow + (size_t)(s.w - 4 - x0) * 4);
         stg128(pd, make_uint4(v.w, v.z, v.y, v.x));
         return;
     }
-    for (int i = 0; i < 4 && x0 + i < d.w; i++) {
+    for (int i = 0; i < PX && x0 + i < d.w; i++) {
         const uint8_t *q = srow + (size_t)(s.w - 1 - x0 - i) * BPP;
 #pragma unroll
         for (int c = 0; c < BPP; c++) pd[i * BPP + c] = q[c];
@@ -253,6 +280,7 @@ __host__ __device__ inline int border_idx(int i, int n, int mode) {
 
 }  // namespace gmatb
 #include "gauss_stream.cuh"
+#include "rotate_linear.cuh"
 namespace gmatb {
 
 // ---------------------------------------------------------------------------
@@ -264,8 +292,10 @@ namespace gmatb {
 #define GAUSS_MAXK 31
 struct GaussParams { float kx[GAUSS_MAXK], ky[GAUSS_MAXK]; int kw, kh, border; };
 
+// Produces the destination columns [xa, xb) only (the whole row, or a frame-edge strip beside the
+// streaming kernel's interior).
 template <int BPP>
-__global__ void __launch_bounds__(256) gaussian_kernel(PImg s, PImg d, GaussParams G) {
+__global__ void __launch_bounds__(256) gaussian_kernel(PImg s, PImg d, GaussParams G, int xa, int xb) {
     extern __shared__ unsigned char gsm[];
     const int TW = 32, TH = 16;
     const int rx = G.kw / 2, ry = G.kh / 2;
@@ -273,7 +303,7 @@ __global__ void __launch_bounds__(256) gaussian_kernel(PImg s, PImg d, GaussPara
     uint8_t *tile = gsm;                                                  // [shh][sw][BPP]
     float *hbuf = reinterpret_cast<float *>(gsm + (((size_t)shh * sw * BPP + 15) & ~(size_t)15));   // [shh][TW][BPP]
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = xa + blockIdx.x * TW, y0 = blockIdx.y * TH;
     const long long fz = blockIdx.z;
     const uint8_t *ps = s.p + fz * s.bstride;
     for (int i = tid; i < sw * shh; i += 256) {
@@ -306,7 +336,7 @@ __global__ void __launch_bounds__(256) gaussian_kernel(PImg s, PImg d, GaussPara
     __syncthreads();
     for (int i = tid; i < TH * TW; i += 256) {
         const int ty = i / TW, tx = i - ty * TW;
-        if (x0 + tx >= d.w || y0 + ty >= d.h) continue;
+        if (x0 + tx >= xb || y0 + ty >= d.h) continue;
         float acc[BPP];
 #pragma unroll
         for (int c = 0; c < BPP; c++) acc[c] = 0.0f;
@@ -444,10 +474,15 @@ extern "C" int gmatb_flip(const GmatbImage *src, const GmatbImage *dst, int code
         dim3 g((d.w * d.bpp + 511) / 512, (d.h + 7) / 8, nbatch(src));
         flip_rows_kernel<<<g, b, 0, st>>>(s, d, vec);
     } else {
-        dim3 g((d.w + 127) / 128, (d.h + 7) / 8, nbatch(src));
-        const int v4 = vec && (d.w % 4 == 0);
-        if (d.bpp == 3) flip_cols_kernel<3><<<g, b, 0, st>>>(s, d, code < 0, v4);
-        else            flip_cols_kernel<4><<<g, b, 0, st>>>(s, d, code < 0, v4);
+        const int v4 = d.w % 4 == 0 && (d.bpp == 4 ? vec : (s.pitch % 4 == 0 && d.pitch % 4 == 0 && ((uintptr_t)s.p | (uintptr_t)d.p | (uintptr_t)s.bstride | (uintptr_t)d.bstride) % 4 == 0));
+        if (d.bpp == 3 && vec && d.w % 16 == 0) {
+            dim3 g((d.w + 511) / 512, (d.h + 7) / 8, nbatch(src));
+            flip_cols_kernel<3, 16><<<g, b, 0, st>>>(s, d, code < 0, 2);
+        } else {
+            dim3 g((d.w + 127) / 128, (d.h + 7) / 8, nbatch(src));
+            if (d.bpp == 3) flip_cols_kernel<3, 4><<<g, b, 0, st>>>(s, d, code < 0, v4);
+            else            flip_cols_kernel<4, 4><<<g, b, 0, st>>>(s, d, code < 0, v4);
+        }
     }
     count_launch();
     return set_cuda_error(cudaGetLastError());
@@ -461,6 +496,16 @@ extern "C" int gmatb_rotate(const GmatbImage *src, const GmatbImage *dst, double
     RotParams R;
     const double rad = angle_deg * 3.14159265358979323846 / 180.0;
     R.c = cos(rad); R.s = sin(rad); R.shx = shift_x; R.shy = shift_y; R.interp = interp;
+    const uintptr_t sal = (uintptr_t)s.p | (uintptr_t)s.pitch | (uintptr_t)s.bstride;
+    const uintptr_t dal = (uintptr_t)d.p | (uintptr_t)d.pitch | (uintptr_t)d.bstride;
+    if ((interp == GMATB_INTERP_LINEAR || interp == GMATB_INTERP_AREA) && d.w % 4 == 0 && s.w >= 2 &&
+        (sal & 3) == 0 && (dal & (d.bpp == 3 ? 3 : 15)) == 0) {
+        dim3 b4(8, 32), g4((d.w / 4 + 7) / 8, (d.h + 31) / 32, nbatch(src));
+        if (d.bpp == 3) rotate_linear4_kernel<3><<<g4, b4, 0, (cudaStream_t)stream>>>(s, d, R);
+        else            rotate_linear4_kernel<4><<<g4, b4, 0, (cudaStream_t)stream>>>(s, d, R);
+        count_launch();
+        return set_cuda_error(cudaGetLastError());
+    }
     dim3 b(32, 8), g((d.w + 31) / 32, (d.h + 7) / 8, nbatch(src));
     if (d.bpp == 3) rotate_kernel<3><<<g, b, 0, (cudaStream_t)stream>>>(s, d, R);
     else            rotate_kernel<4><<<g, b, 0, (cudaStream_t)stream>>>(s, d, R);
@@ -490,22 +535,45 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
     // OpenCV / CV-CUDA rule: sigmaY <= 0 takes sigmaX; a sigma <= 0 is derived from its kernel size
     gauss_weights(kw, sigma_x, G.kx);
     gauss_weights(kh, sigma_y > 0.0 ? sigma_y : sigma_x, G.ky);
-    if ((kw == 3 || kw == 5 || kw == 7) && (kh == 3 || kh == 5 || kh == 7) && s.w >= 4 + kw) {
+    const int sw = 32 + kw - 1, sh = 16 + kh - 1;
+    const size_t smem = (((size_t)sh * sw * d.bpp + 15) & ~(size_t)15) + (size_t)sh * 32 * d.bpp * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = nbatch(src);
+    // generic tile kernel on destination columns [xa, xb)
+    auto tiles = [&](int xa, int xb) -> cudaError_t {
+        if (xb <= xa) return cudaSuccess;
+        dim3 b(32, 8), g((xb - xa + 31) / 32, (d.h + 15) / 16, nb);
+        cudaError_t e = cudaSuccess;
+        if (d.bpp == 3) {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(gaussian_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) gaussian_kernel<3><<<g, b, smem, st>>>(s, d, G, xa, xb);
+        } else {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(gaussian_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) gaussian_kernel<4><<<g, b, smem, st>>>(s, d, G, xa, xb);
+        }
+        if (e == cudaSuccess) { count_launch(); e = cudaGetLastError(); }
+        return e;
+    };
+    const bool words = ((((uintptr_t)s.p | (uintptr_t)s.pitch | (uintptr_t)s.bstride | (uintptr_t)d.p | (uintptr_t)d.pitch | (uintptr_t)d.bstride) & 3) == 0);
+    const int rx = kw / 2;
+    // streaming kernel: 4-pixel strips whose window [4t - rx, 4t + 4 + rx) lies inside the row
+    const int t0 = (rx + 3) / 4, t1 = (d.w - rx - 4) / 4 + 1;
+    if ((kw == 3 || kw == 5 || kw == 7) && (kh == 3 || kh == 5 || kh == 7) && words && t1 > t0) {
         GaussS S;
         memset(&S, 0, sizeof(S));
         for (int i = 0; i < kw; i++) S.kx[i] = G.kx[i];
         for (int i = 0; i < kh; i++) S.ky[i] = G.ky[i];
         S.border = border;
-        const int nb = nbatch(src);
-        const int wx = (d.w + 3) / 4;                 // threads per row
+        const int wx = t1 - t0;                       // threads per row
         long long want = 148LL * 16 * 32 * 4;         // threads
         int bands = (int)((want + (long long)wx * nb - 1) / ((long long)wx * nb));
         bands = std::max(1, std::min(bands, (d.h + 31) / 32));
         S.band = (d.h + bands - 1) / bands;
         bands = (d.h + S.band - 1) / S.band;
         dim3 g2((wx + 127) / 128, bands, nb);
-        cudaStream_t st = (cudaStream_t)stream;
-#define GS(B, KW_, KH_) gauss_stream_kernel<B, KW_, KH_><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.w, d.h, S)
+        static const int minb = getenv("GMATB_GAUSS_MINB") ? atoi(getenv("GMATB_GAUSS_MINB")) : 5;
+#define GS(B, KW_, KH_) do { if (minb >= 5) gauss_stream_kernel<B, KW_, KH_, 5><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); \
+        else gauss_stream_kernel<B, KW_, KH_, 4><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); } while (0)
 #define GK(B, KW_) do { if (kh == 3) GS(B, KW_, 3); else if (kh == 5) GS(B, KW_, 5); else GS(B, KW_, 7); } while (0)
 #define GB(B) do { if (kw == 3) GK(B, 3); else if (kw == 5) GK(B, 5); else GK(B, 7); } while (0)
         if (d.bpp == 3) GB(3); else GB(4);
@@ -513,22 +581,12 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
 #undef GK
 #undef GB
         count_launch();
-        return set_cuda_error(cudaGetLastError());
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = tiles(0, 4 * t0);            // left frame-edge strip
+        if (e == cudaSuccess) e = tiles(4 * t1, d.w);          // right frame-edge strip
+        return set_cuda_error(e);
     }
-    const int sw = 32 + kw - 1, sh = 16 + kh - 1;
-    const size_t smem = (((size_t)sh * sw * d.bpp + 15) & ~(size_t)15) + (size_t)sh * 32 * d.bpp * sizeof(float);
-    dim3 b(32, 8), g((d.w + 31) / 32, (d.h + 15) / 16, nbatch(src));
-    cudaError_t e = cudaSuccess;
-    if (d.bpp == 3) {
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(gaussian_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) gaussian_kernel<3><<<g, b, smem, (cudaStream_t)stream>>>(s, d, G);
-    } else {
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(gaussian_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) gaussian_kernel<4><<<g, b, smem, (cudaStream_t)stream>>>(s, d, G);
-    }
-    if (e != cudaSuccess) return set_cuda_error(e);
-    count_launch();
-    return set_cuda_error(cudaGetLastError());
+    return set_cuda_error(tiles(0, d.w));
 }
 
 extern "C" int gmatb_median(const GmatbImage *src, const GmatbImage *dst, int kw, int kh, void *stream) {

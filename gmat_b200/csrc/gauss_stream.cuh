@@ -2,15 +2,18 @@
 // register-streaming like the fused scale kernel: a thread owns 4 pixels of a row strip and
 // walks down a band of rows.
 //   * per source row: (4 + KW - 1) pixels are fetched as aligned 32-bit words (neighbouring
-//     threads overlap -> L1 hits), bytes go to float through PRMT magic numbers + one packed
-//     FADD2, the KW-tap horizontal chain runs packed on component pairs;
+//     threads overlap -> L1 hits) ONE ROW AHEAD of their use, bytes go to float through PRMT
+//     magic numbers + one packed FADD2, the KW-tap horizontal chain runs packed on component pairs;
 //   * vertically every output row has a running accumulator; a source row updates the KH
 //     accumulators it contributes to, in the oracle's tap order (the rows of an output arrive
 //     in increasing tap index), the one that completes is rounded (FADD magic, ties-to-even =
 //     rintf), packed and stored.  No shared memory, no barriers.
+//   * only strips whose whole window lies inside the row run here (thread index t0 <= t < t1); the
+//     few frame-edge columns, unaligned images and any other kernel size use gaussian_kernel
+//     (filters.cu), so this kernel carries no horizontal border code at all.  Rows above / below
+//     the frame map through border_idx (out-of-line, executed only by the first / last band).
 // Arithmetic is exactly oracle/gmat_oracle.c orc_gaussian: acc = fmaf(k[i], v, acc) from 0.0f,
-// horizontal then vertical, rintf, saturate.  Frame-border strips and any other kernel size use
-// gaussian_kernel (filters.cu).
+// horizontal then vertical, rintf, saturate.
 #pragma once
 #include "common.cuh"
 
@@ -18,24 +21,24 @@ namespace gmatb {
 
 struct GaussS { float kx[7], ky[7]; int border; int band; };
 
-template <int BPP, int KW, int KH>
-__global__ void __launch_bounds__(128) gauss_stream_kernel(const uint8_t *sp, int spitch, long long sbs,
-                                                            uint8_t *dp, int dpitch, long long dbs, int W, int H, GaussS G) {
+__device__ __noinline__ int border_row(int y, int H, int mode) { return border_idx(y, H, mode); }
+
+template <int BPP, int KW, int KH, int MINB>
+__global__ void __launch_bounds__(128, MINB) gauss_stream_kernel(const uint8_t *sp, int spitch, long long sbs,
+                                                               uint8_t *dp, int dpitch, long long dbs, int H, int t0, int t1, GaussS G) {
     constexpr int RX = KW / 2, RY = KH / 2, NPX = 4;
     constexpr int NWIN = (NPX + KW - 1) * BPP;                   // window components per row
     constexpr int NOUT = NPX * BPP;                              // output components per row (12 or 16)
     constexpr int WOFF = RX * BPP;                               // bytes before the strip
     constexpr int WSH = (4 - (WOFF & 3)) & 3;                    // window starts WSH bytes into the first aligned word
     constexpr int NWORDS = (WSH + NWIN + 3) / 4;
-    const int lane_x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int x0 = lane_x * NPX;
-    if (x0 >= W) return;
+    const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const int x0 = t * NPX;
     const long long fz = blockIdx.z;
     const int y_begin = blockIdx.y * G.band, y_end = min(y_begin + G.band, H);
-    const uint8_t *ps = sp + fz * sbs;
-    uint8_t *pd = dp + fz * dbs;
-    const bool interior = (x0 - RX >= 0) && (x0 + NPX + RX <= W) && ((((uintptr_t)ps | (uintptr_t)spitch) & 3) == 0);
-    const bool full_out = x0 + NPX <= W;
+    const uint8_t *ps = sp + fz * sbs + (size_t)x0 * BPP - WOFF - WSH;      // word aligned (host checks)
+    uint8_t *pd = dp + fz * dbs + (size_t)x0 * BPP;
 
     f2 acc[KH][NOUT / 2];
 #pragma unroll
@@ -44,39 +47,35 @@ __global__ void __launch_bounds__(128) gauss_stream_kernel(const uint8_t *sp, in
         for (int o = 0; o < NOUT / 2; o++) acc[a][o] = 0ull;
 
     const int nrows = (y_end - y_begin) + KH - 1;
+    uint32_t w[NWORDS], wn[NWORDS];
+    auto fetch = [&](int i, uint32_t (&dst)[NWORDS]) {
+        int sy = y_begin - RY + i;
+        if ((unsigned)sy >= (unsigned)H) sy = border_row(sy, H, G.border);
+        if (sy < 0 || i >= nrows) {                              // BORDER_CONSTANT row: zeros
+#pragma unroll
+            for (int k = 0; k < NWORDS; k++) dst[k] = 0u;
+        } else {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(ps + (size_t)sy * spitch);
+#pragma unroll
+            for (int k = 0; k < NWORDS; k++) dst[k] = __ldg(q + k);
+        }
+    };
+    fetch(0, w);
     for (int i0 = 0; i0 < nrows; i0 += KH) {
 #pragma unroll
         for (int ph = 0; ph < KH; ph++) {
             const int i = i0 + ph;
             if (i >= nrows) break;
-            const int sy = border_idx(y_begin - RY + i, H, G.border);
+            fetch(i + 1, wn);
             // ---- window of this row as floats: even-aligned pairs E, odd-aligned pairs O (BPP 3 needs both) ----
             f2 E[(NWIN + 1) / 2], O[(NWIN + 1) / 2];
-            if (sy < 0) {
-#pragma unroll
-                for (int j = 0; j < (NWIN + 1) / 2; j++) { E[j] = 0ull; O[j] = 0ull; }
-            } else {
+            {
                 float m[NWIN + 1];
-                const uint8_t *row = ps + (size_t)sy * spitch;
-                if (interior) {
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * BPP - WOFF - WSH);
-                    uint32_t w[NWORDS];
 #pragma unroll
-                    for (int k = 0; k < NWORDS; k++) w[k] = __ldg(q + k);
-#pragma unroll
-                    for (int c = 0; c < NWIN; c++) {
-                        const int b = WSH + c;
-                        m[c] = (b & 3) == 0 ? byte_magic<0>(w[b >> 2]) : (b & 3) == 1 ? byte_magic<1>(w[b >> 2])
-                             : (b & 3) == 2 ? byte_magic<2>(w[b >> 2]) : byte_magic<3>(w[b >> 2]);
-                    }
-                } else {
-#pragma unroll
-                    for (int p = 0; p < NPX + KW - 1; p++) {
-                        const int sx = border_idx(x0 - RX + p, W, G.border);
-#pragma unroll
-                        for (int c = 0; c < BPP; c++)
-                            m[p * BPP + c] = __uint_as_float(0x4B000000u | (sx < 0 ? 0u : (unsigned)row[(size_t)sx * BPP + c]));
-                    }
+                for (int c = 0; c < NWIN; c++) {
+                    const int b = WSH + c;
+                    m[c] = (b & 3) == 0 ? byte_magic<0>(w[b >> 2]) : (b & 3) == 1 ? byte_magic<1>(w[b >> 2])
+                         : (b & 3) == 2 ? byte_magic<2>(w[b >> 2]) : byte_magic<3>(w[b >> 2]);
                 }
                 m[NWIN] = GMATB_MAGIC;
 #pragma unroll
@@ -108,8 +107,7 @@ __global__ void __launch_bounds__(128) gauss_stream_kernel(const uint8_t *sp, in
             }
             // the accumulator that just received tap KH-1 is complete: output row y = y_begin + i - (KH-1)
             const int yo = y_begin + i - (KH - 1);
-            if (yo >= y_begin && yo < y_end) {
-                constexpr int slot = 0;   // placeholder (overridden below per phase)
+            if (yo >= y_begin) {
                 const int sl = (ph - (KH - 1) + KH) % KH;
                 uint32_t r[NOUT];
 #pragma unroll
@@ -118,23 +116,18 @@ __global__ void __launch_bounds__(128) gauss_stream_kernel(const uint8_t *sp, in
                     upki(add2(acc[sl][o], bc(GMATB_MAGIC)), b0, b1);          // 2^23 + rint(v): low byte = pixel (v in [0,255.0x])
                     r[2 * o] = (uint32_t)b0; r[2 * o + 1] = (uint32_t)b1;
                 }
-                (void)slot;
-                uint8_t *q = pd + (size_t)yo * dpitch + (size_t)x0 * BPP;
-                if (full_out && ((((uintptr_t)pd | (uintptr_t)dpitch) & 3) == 0)) {
+                uint32_t *q = reinterpret_cast<uint32_t *>(pd + (size_t)yo * dpitch);
 #pragma unroll
-                    for (int wv = 0; wv < NOUT / 4; wv++) {
-                        uint32_t lo, hi, word;
-                        asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(r[4 * wv]), "r"(r[4 * wv + 1]));
-                        asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(r[4 * wv + 2]), "r"(r[4 * wv + 3]));
-                        asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(word) : "r"(lo), "r"(hi));
-                        reinterpret_cast<uint32_t *>(q)[wv] = word;
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < NOUT; c++)
-                        if (x0 + c / BPP < W) q[c] = (uint8_t)(r[c] & 0xFFu);
+                for (int wv = 0; wv < NOUT / 4; wv++) {
+                    uint32_t lo, hi, word;
+                    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(r[4 * wv]), "r"(r[4 * wv + 1]));
+                    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(r[4 * wv + 2]), "r"(r[4 * wv + 3]));
+                    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(word) : "r"(lo), "r"(hi));
+                    q[wv] = word;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < NWORDS; k++) w[k] = wn[k];
         }
     }
 }

@@ -1,0 +1,120 @@
+// rotate_linear.cuh -- bilinear rotate for word-aligned packed images, 4 destination pixels per thread.
+//
+// Same arithmetic as rotate_kernel / oracle orc_rotate (P-FILTERS): coordinates in double
+// (dy*s and dy*c are shared by the 4 pixels of a thread, every product and sum individually
+// rounded), the four taps fetched as aligned words + funnel shift, byte -> float through PRMT
+// magic numbers, weights and the 4-term blend in the oracle's operation order but packed two
+// pixels at a time on FFMA2, round-to-nearest-even by adding 1.5*2^23, 12 / 16 output bytes
+// stored as words.  The general kernel needs ~125 instructions per pixel (it is issue bound);
+// this one ~60.
+#pragma once
+#include "common.cuh"
+
+namespace gmatb {
+
+#define GMATB_MAGIC15 12582912.0f   /* 1.5 * 2^23: RN(v + M) - M = rint(v), bits(v + M) - bits(M) = (int)rint(v) for |v| < 2^22 */
+
+// the two horizontally adjacent pixels starting `off` bytes into the (word-aligned) frame as magic
+// floats (2^23 + byte): aligned words + funnel shift
+template <int BPP>
+__device__ __forceinline__ void rot_fetch2(const uint8_t *ps, uint32_t off, float (&pa)[BPP], float (&pb)[BPP]) {
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(ps + (off & ~3u));
+    if (BPP == 4) {
+        const uint32_t v0 = __ldg(q), v1 = __ldg(q + 1);
+        pa[0] = byte_magic<0>(v0); pa[1] = byte_magic<1>(v0); pa[2] = byte_magic<2>(v0); pa[BPP - 1] = byte_magic<3>(v0);
+        pb[0] = byte_magic<0>(v1); pb[1] = byte_magic<1>(v1); pb[2] = byte_magic<2>(v1); pb[BPP - 1] = byte_magic<3>(v1);
+    } else {
+        const unsigned sh = (off & 3u) * 8;
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+        const uint32_t w2 = sh == 24 ? __ldg(q + 2) : 0u;      // bytes 6..8 past q only when misaligned by 3
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+        pa[0] = byte_magic<0>(v0); pa[1] = byte_magic<1>(v0); pa[2] = byte_magic<2>(v0);
+        pb[0] = byte_magic<3>(v0); pb[1] = byte_magic<0>(v1); pb[2] = byte_magic<1>(v1);
+    }
+}
+
+template <int BPP>
+__global__ void __launch_bounds__(256) rotate_linear4_kernel(PImg s, PImg d, RotParams R) {
+    // thread = 4 consecutive destination pixels; warp = 8 threads x 4 rows (32x4 pixels), CTA 32x32
+    const int x0 = (blockIdx.x * 8 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 32 + threadIdx.y;
+    if (x0 >= d.w || y >= d.h) return;              // host guarantees d.w % 4 == 0
+    const long long fz = blockIdx.z;
+    const uint8_t *ps = s.p + fz * s.bstride;
+    const int W = s.w, H = s.h;
+    const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+    const double dy = __dsub_rn((double)y, R.shy);
+    const double dys = __dmul_rn(dy, R.s), dyc = __dmul_rn(dy, R.c);
+    const double xd = (double)x0;
+
+    float m[4][2][2][BPP];        // [pixel][row][tap][component], magic floats
+    float sx[4], sy[4], fx1[4], fy1[4];
+    bool valid[4];
+    bool lowside = false;         // a coordinate in (-0.5, 0): weights leave [0,1], the result needs the saturation
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double dx = __dsub_rn(__dadd_rn(xd, (double)i), R.shx);
+        sx[i] = (float)__dsub_rn(__dmul_rn(dx, R.c), dys);
+        sy[i] = (float)__dadd_rn(__dmul_rn(dx, R.s), dyc);
+        valid[i] = sx[i] > -0.5f && sx[i] < Wf && sy[i] > -0.5f && sy[i] < Hf;
+        lowside |= valid[i] && (sx[i] < 0.0f || sy[i] < 0.0f);
+        // truncation through the 2^23 magic number (the F2I / I2F units are 8x slower than the FP32 pipe);
+        // pixels outside the frame get clamped coordinates: their loads stay in range, their result is discarded
+        const float xm = __fadd_rz(fminf(fmaxf(sx[i], 0.0f), Wm1), GMATB_MAGIC);
+        const float ym = __fadd_rz(fminf(fmaxf(sy[i], 0.0f), Hm1), GMATB_MAGIC);
+        const int x1 = __float_as_int(xm) - 0x4B000000, y1 = __float_as_int(ym) - 0x4B000000;
+        fx1[i] = __fadd_rn(xm, -GMATB_MAGIC); fy1[i] = __fadd_rn(ym, -GMATB_MAGIC);
+        // the tap pair (x1, x1+1) of rows y1 and min(y1+1, H-1); in the last source column the pair is fetched one
+        // pixel to the left and its right-hand pixel serves both taps (x2r = W - 1)
+        const uint32_t off0 = (uint32_t)y1 * (uint32_t)s.pitch + (uint32_t)min(x1, W - 2) * BPP;
+        const uint32_t off1 = off0 + (y1 < H - 1 ? (uint32_t)s.pitch : 0u);
+        rot_fetch2<BPP>(ps, off0, m[i][0][0], m[i][0][1]);
+        rot_fetch2<BPP>(ps, off1, m[i][1][0], m[i][1][1]);
+        if (x1 > W - 2) {
+#pragma unroll
+            for (int c = 0; c < BPP; c++) { m[i][0][0][c] = m[i][0][1][c]; m[i][1][0][c] = m[i][1][1][c]; }
+        }
+    }
+    uint32_t ob[4][BPP];          // result bytes (low byte of each word)
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+        const f2 sx2 = pk(sx[i], sx[i + 1]), sy2 = pk(sy[i], sy[i + 1]);
+        const f2 fx2 = pk(fx1[i], fx1[i + 1]), fy2 = pk(fy1[i], fy1[i + 1]);
+        const f2 neg1 = bc(-1.0f);
+        // ax = (x1 + 1) - sx, bx = sx - x1 (and the same in y): a - b as FFMA2(b, -1, a), exact product, one rounding
+        const f2 ax = fma2(sx2, neg1, add2(fx2, bc(1.0f))), bx = fma2(fx2, neg1, sx2);
+        const f2 ay = fma2(sy2, neg1, add2(fy2, bc(1.0f))), by = fma2(fy2, neg1, sy2);
+        const f2 w00 = mul2(ax, ay), w01 = mul2(bx, ay), w10 = mul2(ax, by), w11 = mul2(bx, by);
+#pragma unroll
+        for (int c = 0; c < BPP; c++) {
+            const f2 nm = bc(-GMATB_MAGIC);
+            const f2 p00 = add2(pk(m[i][0][0][c], m[i + 1][0][0][c]), nm), p01 = add2(pk(m[i][0][1][c], m[i + 1][0][1][c]), nm);
+            const f2 p10 = add2(pk(m[i][1][0][c], m[i + 1][1][0][c]), nm), p11 = add2(pk(m[i][1][1][c], m[i + 1][1][1][c]), nm);
+            f2 a = mul2(p00, w00);
+            a = fma2(p01, w01, a);
+            a = fma2(p10, w10, a);
+            a = fma2(p11, w11, a);
+            int b0, b1;
+            upki(add2(a, bc(GMATB_MAGIC15)), b0, b1);
+            if (lowside) {       // rare: saturate (weights outside [0,1] near the top/left frame edge)
+                b0 = min(max(b0 - 0x4B400000, 0), 255); b1 = min(max(b1 - 0x4B400000, 0), 255);
+            }
+            ob[i][c] = valid[i] ? (uint32_t)b0 : 0u;
+            ob[i + 1][c] = valid[i + 1] ? (uint32_t)b1 : 0u;
+        }
+    }
+    uint8_t *pd = d.p + fz * d.bstride + (size_t)y * d.pitch + (size_t)x0 * BPP;
+    auto pack4 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t e) {
+        return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, e, 0x0040), 0x5410);
+    };
+    if (BPP == 3) {
+        stg32(pd,     pack4(ob[0][0], ob[0][1], ob[0][2], ob[1][0]));
+        stg32(pd + 4, pack4(ob[1][1], ob[1][2], ob[2][0], ob[2][1]));
+        stg32(pd + 8, pack4(ob[2][2], ob[3][0], ob[3][1], ob[3][2]));
+    } else {
+        stg128(pd, make_uint4(pack4(ob[0][0], ob[0][1], ob[0][2], ob[0][BPP - 1]), pack4(ob[1][0], ob[1][1], ob[1][2], ob[1][BPP - 1]),
+                              pack4(ob[2][0], ob[2][1], ob[2][2], ob[2][BPP - 1]), pack4(ob[3][0], ob[3][1], ob[3][2], ob[3][BPP - 1])));
+    }
+}
+
+}  // namespace gmatb

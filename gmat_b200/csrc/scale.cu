@@ -291,7 +291,8 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     // shorter than 8 output rows (each band re-converts 2 extra chroma rows)
     long long want = 148LL * 16 * 4;
     int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
-    nb = std::max(1, std::min(nb, (c->dstH + 7) / 8));
+    static const int min_band = getenv("GMATB_FUSED_MINBAND") ? atoi(getenv("GMATB_FUSED_MINBAND")) : 8;
+    nb = std::max(1, std::min(nb, (c->dstH + min_band - 1) / min_band));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
     dim3 g(warps_x, nb, batch);

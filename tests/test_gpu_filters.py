@@ -13,7 +13,7 @@ from gpu_util import assert_same
 
 pytestmark = pytest.mark.gpu
 FMTS = [FMT.RGB24, FMT.BGRA]
-SIZES = [(64, 48), (33, 17), (130, 7), (1, 1), (640, 360)]
+SIZES = [(64, 48), (33, 17), (130, 7), (132, 9), (1, 1), (640, 360)]
 
 
 def pair(fmt, w, h, dev, n=1, seed=1):

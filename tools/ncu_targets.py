@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""a few launches of the kernels we want ncu captures of (run under ncu with -k filters)"""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import gmat_b200 as g
+from gmat_b200 import FMT, SWS, BORDER, INTERP, FrameBatch, SwsContext
+dev = torch.device("cuda:0"); B = 16
+HW = SWS.HWACCEL_CUDA
+src = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); src.buf.random_(0, 256)
+d1080 = FrameBatch(FMT.RGB24, 1920, 1080, B, device=dev)
+d720 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
+which = sys.argv[1:] or ["fused", "bilinear", "generic", "rotate", "gauss", "median", "rgb2yuv", "fliph"]
+if "fused" in which:
+    SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | HW, (0.75,)).scale(src, d1080)
+if "bilinear" in which:
+    SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BILINEAR | HW).scale(src, d1080)
+if "generic" in which:
+    SwsContext(3840, 2160, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | HW).scale(src, d720)
+a = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev); a.buf.random_(0, 256)
+b = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev)
+if "rotate" in which:
+    g.rotate(a, b, 30.0, 0.0, 0.0, INTERP.LINEAR)
+if "gauss" in which:
+    g.gaussian(a, b, 5, 5, 1.1, 1.1, BORDER.REFLECT101)
+if "median" in which:
+    g.median(a, b, 3, 3)
+if "rgb2yuv" in which:
+    back = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); g.rgb2yuv(a, back)
+if "fliph" in which:
+    g.flip(a, b, 1)
+torch.cuda.synchronize()
