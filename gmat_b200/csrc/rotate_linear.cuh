@@ -18,7 +18,7 @@ namespace gmatb {
 // floats (2^23 + byte): aligned words + funnel shift
 template <int BPP>
 __device__ __forceinline__ void rot_fetch2(const uint8_t *ps, uint32_t off, float (&pa)[BPP], float (&pb)[BPP]) {
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(ps + (off & ~3u));
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(ps) + (off >> 2);
     if (BPP == 4) {
         const uint32_t v0 = __ldg(q), v1 = __ldg(q + 1);
         pa[0] = byte_magic<0>(v0); pa[1] = byte_magic<1>(v0); pa[2] = byte_magic<2>(v0); pa[BPP - 1] = byte_magic<3>(v0);
@@ -31,6 +31,30 @@ __device__ __forceinline__ void rot_fetch2(const uint8_t *ps, uint32_t off, floa
         pa[0] = byte_magic<0>(v0); pa[1] = byte_magic<1>(v0); pa[2] = byte_magic<2>(v0);
         pb[0] = byte_magic<3>(v0); pb[1] = byte_magic<0>(v1); pb[2] = byte_magic<1>(v1);
     }
+}
+
+// One pixel in the oracle's scalar form: the rare cases the packed path does not cover -- a coordinate in
+// (-0.5, 0) (weights leave [0,1]: the result needs the saturation) or the last source column (both
+// horizontal taps are pixel W-1).  Out of line so that it costs the common path nothing.
+template <int BPP>
+__device__ __noinline__ uint32_t rot_slow_pixel(const uint8_t *ps, int pitch, int W, int H, float sx, float sy) {
+    const int x1 = __float2int_rz(sx), y1 = __float2int_rz(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int x2r = min(x2, W - 1), y2r = min(y2, H - 1);
+    const float ax = __fsub_rn((float)x2, sx), bx = __fsub_rn(sx, (float)x1);
+    const float ay = __fsub_rn((float)y2, sy), by = __fsub_rn(sy, (float)y1);
+    const float w00 = __fmul_rn(ax, ay), w01 = __fmul_rn(bx, ay), w10 = __fmul_rn(ax, by), w11 = __fmul_rn(bx, by);
+    const uint8_t *r0 = ps + (size_t)y1 * pitch, *r1 = ps + (size_t)y2r * pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < BPP; c++) {
+        float a = __fmul_rn((float)r0[(size_t)x1 * BPP + c], w00);
+        a = __fmaf_rn((float)r0[(size_t)x2r * BPP + c], w01, a);
+        a = __fmaf_rn((float)r1[(size_t)x1 * BPP + c], w10, a);
+        a = __fmaf_rn((float)r1[(size_t)x2r * BPP + c], w11, a);
+        out |= (uint32_t)min(max(__float2int_rn(a), 0), 255) << (8 * c);
+    }
+    return out;
 }
 
 template <int BPP>
@@ -49,31 +73,25 @@ __global__ void __launch_bounds__(256) rotate_linear4_kernel(PImg s, PImg d, Rot
 
     float m[4][2][2][BPP];        // [pixel][row][tap][component], magic floats
     float sx[4], sy[4], fx1[4], fy1[4];
-    bool valid[4];
-    bool lowside = false;         // a coordinate in (-0.5, 0): weights leave [0,1], the result needs the saturation
+    bool valid[4], special[4];    // special: handled by rot_slow_pixel
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const double dx = __dsub_rn(__dadd_rn(xd, (double)i), R.shx);
         sx[i] = (float)__dsub_rn(__dmul_rn(dx, R.c), dys);
         sy[i] = (float)__dadd_rn(__dmul_rn(dx, R.s), dyc);
         valid[i] = sx[i] > -0.5f && sx[i] < Wf && sy[i] > -0.5f && sy[i] < Hf;
-        lowside |= valid[i] && (sx[i] < 0.0f || sy[i] < 0.0f);
         // truncation through the 2^23 magic number (the F2I / I2F units are 8x slower than the FP32 pipe);
         // pixels outside the frame get clamped coordinates: their loads stay in range, their result is discarded
         const float xm = __fadd_rz(fminf(fmaxf(sx[i], 0.0f), Wm1), GMATB_MAGIC);
         const float ym = __fadd_rz(fminf(fmaxf(sy[i], 0.0f), Hm1), GMATB_MAGIC);
         const int x1 = __float_as_int(xm) - 0x4B000000, y1 = __float_as_int(ym) - 0x4B000000;
         fx1[i] = __fadd_rn(xm, -GMATB_MAGIC); fy1[i] = __fadd_rn(ym, -GMATB_MAGIC);
-        // the tap pair (x1, x1+1) of rows y1 and min(y1+1, H-1); in the last source column the pair is fetched one
-        // pixel to the left and its right-hand pixel serves both taps (x2r = W - 1)
+        // the tap pair (x1, x1+1) of rows y1 and min(y1+1, H-1)
+        special[i] = valid[i] && (sx[i] < 0.0f || sy[i] < 0.0f || x1 > W - 2);
         const uint32_t off0 = (uint32_t)y1 * (uint32_t)s.pitch + (uint32_t)min(x1, W - 2) * BPP;
         const uint32_t off1 = off0 + (y1 < H - 1 ? (uint32_t)s.pitch : 0u);
         rot_fetch2<BPP>(ps, off0, m[i][0][0], m[i][0][1]);
         rot_fetch2<BPP>(ps, off1, m[i][1][0], m[i][1][1]);
-        if (x1 > W - 2) {
-#pragma unroll
-            for (int c = 0; c < BPP; c++) { m[i][0][0][c] = m[i][0][1][c]; m[i][1][0][c] = m[i][1][1][c]; }
-        }
     }
     uint32_t ob[4][BPP];          // result bytes (low byte of each word)
 #pragma unroll
@@ -96,13 +114,17 @@ __global__ void __launch_bounds__(256) rotate_linear4_kernel(PImg s, PImg d, Rot
             a = fma2(p11, w11, a);
             int b0, b1;
             upki(add2(a, bc(GMATB_MAGIC15)), b0, b1);
-            if (lowside) {       // rare: saturate (weights outside [0,1] near the top/left frame edge)
-                b0 = min(max(b0 - 0x4B400000, 0), 255); b1 = min(max(b1 - 0x4B400000, 0), 255);
-            }
             ob[i][c] = valid[i] ? (uint32_t)b0 : 0u;
             ob[i + 1][c] = valid[i + 1] ? (uint32_t)b1 : 0u;
         }
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (special[i]) {
+            const uint32_t v = rot_slow_pixel<BPP>(ps, s.pitch, W, H, sx[i], sy[i]);
+#pragma unroll
+            for (int c = 0; c < BPP; c++) ob[i][c] = (v >> (8 * c)) & 0xFFu;
+        }
     uint8_t *pd = d.p + fz * d.bstride + (size_t)y * d.pitch + (size_t)x0 * BPP;
     auto pack4 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t e) {
         return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, e, 0x0040), 0x5410);

@@ -53,7 +53,7 @@ def test_rotate(dev, fmt, interp):
     code = {"nearest": 0, "linear": 1, "cubic": 2}[interp]
     for (w, h) in ((64, 48), (33, 17), (640, 360)):
         src, ds = pair(fmt, w, h, dev, 1, seed=w)
-        for ang, sx, sy in ((30.0, 0.0, 0.0), (30.0, -20.5, 11.25), (-77.3, 40.0, 5.0), (180.0, w - 1.0, h - 1.0), (0.0, 0.0, 0.0), (90.0, 0.0, h - 1.0)):
+        for ang, sx, sy in ((30.0, 0.0, 0.0), (30.0, -20.5, 11.25), (-77.3, 40.0, 5.0), (180.0, w - 1.0, h - 1.0), (0.0, 0.0, 0.0), (90.0, 0.0, h - 1.0), (0.5, 0.3, 0.2), (-0.7, -0.4, 0.45)):
             dd = FrameBatch(fmt, w, h, 1, device=dev); g.rotate(ds, dd, ang, sx, sy, interp); torch.cuda.synchronize()
             ref = FrameBatch(fmt, w, h, 1); s, d = src.image(), ref.image()
             orc.orc().orc_rotate(C.byref(s), C.byref(d), ang, sx, sy, code)
