@@ -317,28 +317,49 @@ static int run_generic(GmatbSws *c, int bank, const Img &s, const Img &d, int dW
     P.factor = bits == 8 ? 255.f : 65535.f; P.vmax = P.factor;
     P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
     P.cx = c->cx[bank]; P.cy = c->cy[bank]; P.px = c->px[bank]; P.py = c->py[bank];
-    P.dstW = dW; P.dstH = dH; P.src_kind = src_kind; P.ch = ch; P.dst_code = dst_code; P.sparse = 0;
+    P.dstW = dW; P.dstH = dH; P.src_kind = src_kind; P.ch = ch; P.dst_code = dst_code;
     const std::vector<int> &hx = c->hpx[bank], &hy = c->hpy[bank];
-    int tw = 32, th = 8;
+    const int st = ch == 3 ? 4 : ch;              // floats per pixel in shared memory
+    int tw = 32, th = 64;
     size_t smem = 0;
-    for (;;) {   // shrink the tile until the window fits in shared memory
+    for (;;) {   // shrink the tile until the window fits in shared memory; several CTAs per SM wanted
         int mw = 0, mh = 0;
-        for (int x = 0; x < dW; x += tw) mw = std::max(mw, hx[std::min(x + tw, dW) - 1] + 4 - hx[x]);
-        for (int y = 0; y < dH; y += th) mh = std::max(mh, hy[std::min(y + th, dH) - 1] + 4 - hy[y]);
-        smem = ((size_t)mw * mh + (size_t)mh * tw) * ch * sizeof(float);
+        // the kernel rounds the window origin down (x to 4, y to 2: chroma grid, word loads): measure from there
+        for (int x = 0; x < dW; x += tw) mw = std::max(mw, hx[std::min(x + tw, dW) - 1] + 4 - (hx[x] & ~3));
+        for (int y = 0; y < dH; y += th) mh = std::max(mh, hy[std::min(y + th, dH) - 1] + 4 - (hy[y] & ~1));
+        mw = (mw + 3) & ~3; mh = (mh + 1) & ~1;
+        // window: planar ch floats per pixel for 3/4 components (rounded to 16 bytes), else st; horizontal results: st
+        smem = (st == 4 ? (((size_t)mw * mh * ch + 3) & ~(size_t)3) : (size_t)mw * mh * st) * sizeof(float) + (size_t)mh * tw * st * sizeof(float);
         P.win_w = mw; P.win_h = mh;
-        if (smem <= 160 * 1024 || (tw == 1 && th == 1)) break;
-        if (tw >= th && tw > 1) tw /= 2; else if (th > 1) th /= 2; else tw /= 2;
+        static const size_t budget = (getenv("GMATB_GEN_SMEM") ? atoi(getenv("GMATB_GEN_SMEM")) : 64) * 1024;
+        if (smem <= budget || (tw == 1 && th == 1)) break;
+        if (th > 8) th /= 2; else if (tw >= 2 * th && tw > 8) tw /= 2; else if (th > 1) th /= 2; else tw /= 2;
     }
     if (smem > 200 * 1024) return GMATB_ERR_UNSUPPORTED;
     P.tile_w = tw; P.tile_h = th;
+    P.tile_shift = 0;
+    while ((1 << P.tile_shift) < tw) P.tile_shift++;
+    const int sb = bits / 8;
+    auto al = [](const Plane &pl, int a) { return ((((uintptr_t)pl.p) | (uintptr_t)pl.pitch | (uintptr_t)pl.bstride) & (uintptr_t)(a - 1)) == 0; };
+    P.aligned = src_kind != GS_PACKED && al(s.pl[0], 4 * sb) && al(s.pl[1], src_kind == GS_NV12 ? 4 * sb : 2 * sb) &&
+                (src_kind == GS_NV12 || al(s.pl[2], 2 * sb));
+    P.dst_vec = al(d.pl[0], 4 * sb);
     dim3 g((dW + tw - 1) / tw, (dH + th - 1) / th, batch > 1 ? batch : 1);
     cudaError_t e = cudaSuccess;
-#define GO(B, R) do { \
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(generic_scale_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) generic_scale_kernel<B, R><<<g, 256, smem, c->stream>>>(P); } while (0)
-    if (bits == 8) { if (c->ra) GO(8, 1); else GO(8, 0); }
-    else           { if (c->ra) GO(16, 1); else GO(16, 0); }
+#define GO(S, B, C, R) do { \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(generic_scale_kernel<S, B, C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) generic_scale_kernel<S, B, C, R><<<g, 256, smem, c->stream>>>(P); } while (0)
+#define GO_R(S, B, C) do { if (c->ra) GO(S, B, C, 1); else GO(S, B, C, 0); } while (0)
+#define GO_B(S, C) do { if (bits == 8) GO_R(S, 8, C); else GO_R(S, 16, C); } while (0)
+    if (src_kind == GS_NV12) GO_B(GS_NV12, 3);
+    else if (src_kind == GS_I420) GO_B(GS_I420, 3);
+    else if (ch == 1) GO_B(GS_PACKED, 1);
+    else if (ch == 2) GO_B(GS_PACKED, 2);
+    else if (ch == 3) GO_B(GS_PACKED, 3);
+    else if (ch == 4) GO_B(GS_PACKED, 4);
+    else return GMATB_ERR_UNSUPPORTED;
+#undef GO_B
+#undef GO_R
 #undef GO
     if (e != cudaSuccess) return set_cuda_error(e);
     count_launch();

@@ -32,7 +32,22 @@ for label, flag, param in (("bicubic A=-0.75", SWS.BICUBIC, (0.75,)), ("bicubic 
 g720 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
 cg = SwsContext(3840, 2160, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
 report("generic: 4K NV12->720p RGB24 bicubic (3:1)", timeit(lambda: cg.scale(src, g720), 3), B * 3840 * 2160, B * (12441600 + 2764800))
-del g720
+cg2 = SwsContext(3840, 2160, FMT.NV12, 1280, 720, FMT.RGBA, SWS.LANCZOS | SWS.HWACCEL_CUDA)
+g720a = FrameBatch(FMT.RGBA, 1280, 720, B, device=dev)
+report("generic: 4K NV12->720p RGBA lanczos (3:1)", timeit(lambda: cg2.scale(src, g720a), 3), B * 3840 * 2160, B * (12441600 + 3686400))
+del g720, g720a
+s1080 = FrameBatch(FMT.NV12, 1920, 1080, B, device=dev); s1080.buf.random_(0, 256)
+g7 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
+cg3 = SwsContext(1920, 1080, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
+report("generic: 1080p NV12->720p RGB24 bicubic (1.5:1)", timeit(lambda: cg3.scale(s1080, g7), 3), B * 1920 * 1080, B * (3110400 + 2764800))
+g4k = FrameBatch(FMT.RGB24, 3840, 2160, 16, device=dev)
+cg4 = SwsContext(1920, 1080, FMT.NV12, 3840, 2160, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
+s16 = FrameBatch(FMT.NV12, 1920, 1080, 16, device=dev); s16.buf.random_(0, 256)
+report("generic: 1080p NV12->4K RGB24 bicubic (1:2 up)", timeit(lambda: cg4.scale(s16, g4k), 3), 16 * 1920 * 1080, 16 * (3110400 + 24883200))
+n7 = FrameBatch(FMT.NV12, 1280, 720, B, device=dev)
+cg5 = SwsContext(1920, 1080, FMT.NV12, 1280, 720, FMT.NV12, SWS.BICUBIC | SWS.HWACCEL_CUDA)
+report("generic: 1080p NV12->720p NV12 bicubic (planes)", timeit(lambda: cg5.scale(s1080, n7), 3), B * 1920 * 1080, B * (3110400 + 1382400))
+del g7, g4k, s1080, s16, n7
 d4 = FrameBatch(FMT.RGBA, 1920, 1080, B, device=dev)
 c = SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGBA, SWS.BICUBIC | SWS.HWACCEL_CUDA, (0.75,))
 report("C2 -> RGBA bicubic A=-0.75", timeit(lambda: c.scale(src, d4)), B * 3840 * 2160, B * (12441600 + 8294400))
