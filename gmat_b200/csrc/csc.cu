@@ -188,7 +188,10 @@ __device__ __forceinline__ void store_rgb_px(uint8_t *p, int r, int g, int b) {
 // yuv -> packed rgb
 // ---------------------------------------------------------------------------
 template <int L, int SBITS, int DST, bool SPARSE>
-__global__ void __launch_bounds__(256, 4) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
+#ifndef GMATB_Y2R_MINB
+#define GMATB_Y2R_MINB 4
+#endif
+__global__ void __launch_bounds__(256, GMATB_Y2R_MINB) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (x0 >= src.w || y0 >= src.h) return;
@@ -352,7 +355,10 @@ __host__ __device__ constexpr bool srgb_is16(int s) { return s >= S_RGBA64; }
 // 16-bit rgb -> 8-bit yuv uses the high byte of each component (the reference
 // mis-reads every non-RGB24 source as RGB24, :748-762 -- not reproduced).
 template <int SRC, int L, int DBITS>
-__global__ void __launch_bounds__(256) rgb2yuv_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
+#ifndef GMATB_R2Y_MINB
+#define GMATB_R2Y_MINB 3
+#endif
+__global__ void __launch_bounds__(256, GMATB_R2Y_MINB) rgb2yuv_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     const int W = src.w, H = src.h;

@@ -262,13 +262,19 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     if (c->ra) {      // bilinear 2:1 integer kernel
         if (!planes_aligned(P.src, np, 16) || !planes_aligned(P.dst, 1, (dc == D_RGB24 || dc == D_BGR24) ? 4 : 16)) return 0;
         dim3 g((c->srcW + 255) / 256, (c->srcH / 2 + 7) / 8, src->batch > 1 ? src->batch : 1), b(32, 8);
+        static const int bl_minb = getenv("GMATB_BL_MINB") ? atoi(getenv("GMATB_BL_MINB")) : 6;
+#define BLM(Lx, D) do { if (bl_minb >= 8) fused_csc_bilinear2_kernel<Lx, D, 8><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
+            else if (bl_minb >= 6) fused_csc_bilinear2_kernel<Lx, D, 6><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
+            else if (bl_minb == 5) fused_csc_bilinear2_kernel<Lx, D, 5><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
+            else fused_csc_bilinear2_kernel<Lx, D, 4><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); } while (0)
 #define BL(Lx) do { switch (dc) { \
-            case D_RGB24: fused_csc_bilinear2_kernel<Lx, D_RGB24><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
-            case D_BGR24: fused_csc_bilinear2_kernel<Lx, D_BGR24><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
-            case D_RGBA:  fused_csc_bilinear2_kernel<Lx, D_RGBA><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; \
-            default:      fused_csc_bilinear2_kernel<Lx, D_BGRA><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); break; } } while (0)
+            case D_RGB24: BLM(Lx, D_RGB24); break; \
+            case D_BGR24: BLM(Lx, D_BGR24); break; \
+            case D_RGBA:  BLM(Lx, D_RGBA); break; \
+            default:      BLM(Lx, D_BGRA); break; } } while (0)
         if (semi) BL(L_NV12); else BL(L_I420);
 #undef BL
+#undef BLM
         count_launch();
         int rc0 = set_cuda_error(cudaGetLastError());
         *done = (rc0 == 0);

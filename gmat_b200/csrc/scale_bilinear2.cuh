@@ -49,8 +49,8 @@ __device__ __forceinline__ uint32_t lowbytes4(uint32_t a, uint32_t b, uint32_t c
 }
 
 // DST: D_RGB24 / D_BGR24 / D_RGBA / D_BGRA.  Source width % 8 == 0, height even, 16-byte aligned planes.
-template <int L, int DST>
-__global__ void __launch_bounds__(256, 4) fused_csc_bilinear2_kernel(Img src, Img dst, Mat9 M) {
+template <int L, int DST, int MINB>
+__global__ void __launch_bounds__(256, MINB) fused_csc_bilinear2_kernel(Img src, Img dst, Mat9 M) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (x0 >= src.w || y0 >= src.h) return;

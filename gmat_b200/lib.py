@@ -40,7 +40,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgmat_b200.so")
+    # GMATB_LIB: an alternative build of the same library (kernel tuning experiments, tools/)
+    return os.environ.get("GMATB_LIB") or os.path.join(_HERE, "libgmat_b200.so")
 
 
 def lib():
