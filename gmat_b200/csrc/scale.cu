@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "scale_fused.cuh"
+#include "scale_fused3.cuh"
 #include "scale_bilinear2.cuh"
 #include "scale_generic.cuh"
 
@@ -203,17 +203,18 @@ static NormK norm_k(int bits) {
     return k;
 }
 
-// MINB = resident warps per SM the register allocation must allow (__launch_bounds__(32, MINB)).
-// Measured on B200 (C2, A=-0.75): 16/20 -> 707 Gpx/s, 24/28/32 (spilling) -> 660.  20 it is.
+// MINB = resident warps per SM the register allocation must allow (__launch_bounds__(32, MINB)):
+// 16 -> 128 registers, the v3 kernel needs ~120 to keep every constant and both row-pair buffers
+// resident (at 96 it spills and rematerialises parameters inside the loop).
 template <int L, int SBITS, int DST>
-static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused2Params &P) {
-#define K(T, W) fused_csc_scale2_kernel<L, SBITS, DST, T, W, 20><<<g, 32, 0, st>>>(P)
+static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
+#define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, 16><<<g, 32, 0, st>>>(P)
     if (wrap) { if (taps2) K(true, true); else K(false, true); }
     else      { if (taps2) K(true, false); else K(false, false); }
 #undef K
 }
 template <int L, int SBITS>
-static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused2Params &P) {
+static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
     if (SBITS == 8) {
         switch (dc) {
         case D_RGB24: launch_fused_t<L, SBITS, D_RGB24>(taps2, wrap, g, st, P); break;
@@ -252,7 +253,7 @@ static bool planes_aligned(const Img &a, int np, int al) {
 
 static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
     *done = false;
-    Fused2Params P;
+    Fused3Params P;
     const int np = is_yuv(src->format) ? fmt_planes(src->format) : 1;
     if (!to_img(src, &P.src, np) || !to_img(dst, &P.dst, 1)) return GMATB_ERR_INVAL;
     const int bits = fmt_bits(src->format);
@@ -285,14 +286,16 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     if (!rgbsrc && (semi ? !planes_aligned(P.src, 2, bits == 8 ? 8 : 16) : !(planes_aligned(P.src, 3, bits == 8 ? 4 : 8)))) return 0;
     const int dal = (dc == D_RGB24 || dc == D_BGR24) ? 4 : (dc == D_RGB48 || dc == D_BGR48) ? 8 : 16;
     if (!planes_aligned(P.dst, 1, dal)) return 0;
-    P.M = c->M;
+    P.cm45[0] = c->M.m[4]; P.cm45[1] = c->M.m[5]; P.cm72[0] = c->M.m[7]; P.cm72[1] = c->M.m[2];
+    P.m0 = c->M.m[0]; P.m1 = c->M.m[1]; P.m3 = c->M.m[3]; P.m6 = c->M.m[6];
     for (int i = 0; i < 4; i++) { P.wx[i] = c->wx[i]; P.wy[i] = c->wy[i]; }
     P.nk = norm_k(bits);
     P.factor = bits == 8 ? 255.f : 65535.f;
-    P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
     P.dstW = c->dstW; P.dstH = c->dstH;
     const int batch = src->batch > 1 ? src->batch : 1;
-    const int warps_x = (c->srcW / 8 + 31) / 32;
+    // 4-tap: strips overlap by one lane per side (30 owning lanes per warp); 2-tap: 32
+    const int own = c->taps2 ? 32 : 30;
+    const int warps_x = (c->srcW / 8 + own - 1) / own;
     // enough warps to fill 148 SMs x 16 resident warps a few times over, but bands no
     // shorter than 8 output rows (each band re-converts 2 extra chroma rows)
     long long want = 148LL * 16 * 4;
@@ -303,7 +306,7 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     nb = (c->dstH + P.band - 1) / P.band;
     dim3 g(warps_x, nb, batch);
     int rc;
-    const bool wrap = P.wrap != 0;
+    const bool wrap = (c->flags & GMATB_SWS_PARITY_WRAP) != 0;
     if (rgbsrc) {
         // same component order in and out: run the RGB24 instantiation for both rgb24 and bgr24
         launch_fused_t<L_RGB3, 8, D_RGB24>(c->taps2, wrap, g, c->stream, P);

@@ -360,4 +360,5 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_kernel(const Fused2
     }
 }
 
+
 }  // namespace gmatb
