@@ -209,6 +209,14 @@ static NormK norm_k(int bits) {
 template <int L, int SBITS, int DST>
 static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
 #define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, 16><<<g, 32, 0, st>>>(P)
+    if (L == L_NV12 && SBITS == 8 && DST == D_RGB24 && !wrap) {      // experiment hook: register budget
+        static const int minb = getenv("GMATB_FUSED_MINB") ? atoi(getenv("GMATB_FUSED_MINB")) : 16;
+        if (minb == 20) {
+            if (taps2) fused_csc_scale2_v3_kernel<L_NV12, 8, D_RGB24, true, false, 20><<<g, 32, 0, st>>>(P);
+            else fused_csc_scale2_v3_kernel<L_NV12, 8, D_RGB24, false, false, 20><<<g, 32, 0, st>>>(P);
+            return;
+        }
+    }
     if (wrap) { if (taps2) K(true, true); else K(false, true); }
     else      { if (taps2) K(true, false); else K(false, false); }
 #undef K
@@ -262,20 +270,25 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     const bool rgbsrc = c->kind == K_RGB2RGB;
     if (c->ra) {      // bilinear 2:1 integer kernel
         if (!planes_aligned(P.src, np, 16) || !planes_aligned(P.dst, 1, (dc == D_RGB24 || dc == D_BGR24) ? 4 : 16)) return 0;
-        dim3 g((c->srcW + 255) / 256, (c->srcH / 2 + 7) / 8, src->batch > 1 ? src->batch : 1), b(32, 8);
-        static const int bl_minb = getenv("GMATB_BL_MINB") ? atoi(getenv("GMATB_BL_MINB")) : 6;
-#define BLM(Lx, D) do { if (bl_minb >= 8) fused_csc_bilinear2_kernel<Lx, D, 8><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
-            else if (bl_minb >= 6) fused_csc_bilinear2_kernel<Lx, D, 6><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
-            else if (bl_minb == 5) fused_csc_bilinear2_kernel<Lx, D, 5><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); \
-            else fused_csc_bilinear2_kernel<Lx, D, 4><<<g, b, 0, c->stream>>>(P.src, P.dst, c->M); } while (0)
+        Bl2Params Q;
+        Q.src = P.src; Q.dst = P.dst;
+        Q.cm45[0] = c->M.m[4]; Q.cm45[1] = c->M.m[5]; Q.cm72[0] = c->M.m[7]; Q.cm72[1] = c->M.m[2];
+        Q.m0 = c->M.m[0]; Q.m1 = c->M.m[1]; Q.m3 = c->M.m[3]; Q.m6 = c->M.m[6];
+        const int nbatch = src->batch > 1 ? src->batch : 1;
+        const int wx = (c->srcW / 8 + 31) / 32;
+        // bands: enough warps for 148 SMs x 24 resident warps a few times over, but no shorter than 8 row pairs
+        int nbl = (int)((148LL * 24 * 3 + (long long)wx * nbatch - 1) / ((long long)wx * nbatch));
+        nbl = std::max(1, std::min(nbl, (c->dstH + 7) / 8));
+        Q.band = (c->dstH + nbl - 1) / nbl;
+        nbl = (c->dstH + Q.band - 1) / Q.band;
+        dim3 g(wx, nbl, nbatch);
 #define BL(Lx) do { switch (dc) { \
-            case D_RGB24: BLM(Lx, D_RGB24); break; \
-            case D_BGR24: BLM(Lx, D_BGR24); break; \
-            case D_RGBA:  BLM(Lx, D_RGBA); break; \
-            default:      BLM(Lx, D_BGRA); break; } } while (0)
+            case D_RGB24: fused_csc_bilinear2_stream_kernel<Lx, D_RGB24, 24><<<g, 32, 0, c->stream>>>(Q); break; \
+            case D_BGR24: fused_csc_bilinear2_stream_kernel<Lx, D_BGR24, 24><<<g, 32, 0, c->stream>>>(Q); break; \
+            case D_RGBA:  fused_csc_bilinear2_stream_kernel<Lx, D_RGBA, 24><<<g, 32, 0, c->stream>>>(Q); break; \
+            default:      fused_csc_bilinear2_stream_kernel<Lx, D_BGRA, 24><<<g, 32, 0, c->stream>>>(Q); break; } } while (0)
         if (semi) BL(L_NV12); else BL(L_I420);
 #undef BL
-#undef BLM
         count_launch();
         int rc0 = set_cuda_error(cudaGetLastError());
         *done = (rc0 == 0);

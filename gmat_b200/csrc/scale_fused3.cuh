@@ -128,11 +128,16 @@ struct Fused3 {
     typedef Raw3<L, SBITS> Row;
     static constexpr int SB = SBITS / 8;
 
-    // one row pair k: convert `cur`, finish output row k-1, start output row k
-    static __device__ __forceinline__ void step(const Fused3Params &P, const Row &cur, float (&acc)[4][3], float (&hb_prev)[4][3],
-                                                bool store, uint8_t *pd, int alpha_i) {
+    // one row pair k: convert `cur`, finish output row k-1, start output row k.  `refill(cur)` issues the
+    // loads of the row pair two steps ahead into the same buffer as soon as its raw words are consumed
+    // (measured DRAM latency under load is ~2 steps of a warp's instruction stream at 4 warps/SMSP).
+    template <typename Refill>
+    static __device__ __forceinline__ void step(const Fused3Params &P, Row &cur, float (&acc)[4][3], float (&hb_prev)[4][3],
+                                                bool store, uint8_t *pd, int alpha_i, Refill refill) {
         f2 C[8][3];
-        produce3<L, SBITS>(cur, P, C);
+        const Row now = cur;
+        refill(cur);
+        produce3<L, SBITS>(now, P, C);
         f2 PL[3] = {0ull, 0ull, 0ull}, PR[3] = {0ull, 0ull, 0ull};
         if (!TAPS2) {
 #pragma unroll
@@ -265,30 +270,29 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
     }
 
     // Row pair k finishes output row k-1 (written at pd) and starts row k; pairs yo_begin-1 .. yo_end
-    // are consumed, the first two only prime the accumulators.
+    // are consumed, the first two only prime the accumulators.  A holds pair k, B pair k+1; each step
+    // refills its own buffer with the pair two steps ahead.
     Row A, B;
     int k = yo_begin - 1;
     load_clamped(k, A);
-    // generic trip (rolled; used for the first pair and the last two or three of the band)
+    load_clamped(k + 1, B);
+    // generic trip (rolled; the first pair and the last few of the band): clamped rows, buffers swapped by copy
     auto slow_trip = [&]() {
-        if (k < yo_end) load_clamped(k + 1, B);
-        F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i);
-        A = B; k++; pd += pitch_d;
+        F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i,
+                [&](Row &R) { if (k + 2 <= yo_end) load_clamped(k + 2, R); });
+        const Row t = A; A = B; B = t;
+        k++; pd += pitch_d;
     };
     slow_trip();
-    // steady state: pairs k+1 and k+2 are interior (no clamps): warp-uniform offsets advance by constant
-    // steps, A and B ping-pong (one is converted while the other's loads are in flight)
+    // steady state: pairs k+2 and k+3 are interior (no clamps): warp-uniform offsets advance by constant steps
     {
-        unsigned ot = (unsigned)(2 * k + 2) * pitch_y, ob = ot + pitch_y, oc = (unsigned)(k + 1) * pitch_c, oc2 = (unsigned)(k + 1) * pitch_c2;
+        unsigned ot = (unsigned)(2 * k + 4) * pitch_y, ob = ot + pitch_y, oc = (unsigned)(k + 2) * pitch_c, oc2 = (unsigned)(k + 2) * pitch_c2;
         const unsigned sy = 2 * pitch_y;
-        while (k + 2 <= yo_end - 1) {
-            load_at(B, ot, ob, oc, oc2);
-            ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2;
-            F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i);
+        auto refill = [&](Row &R) { load_at(R, ot, ob, oc, oc2); ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2; };
+        while (k + 3 <= yo_end - 1) {
+            F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i, refill);
             pd += pitch_d;
-            load_at(A, ot, ob, oc, oc2);
-            ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2;
-            F::step(P, B, acc, hb_prev, owner, pd, alpha_i);
+            F::step(P, B, acc, hb_prev, owner, pd, alpha_i, refill);
             pd += pitch_d;
             k += 2;
         }

@@ -147,6 +147,16 @@ __global__ void __launch_bounds__(1024) tput(float *out, float a, float b, int i
             MR(0) MR(1) MR(2) MR(3) MR(4) MR(5) MR(6) MR(7)
         } else if (OP == 30) {  // mix 6 FFMA2(U,U) + 2 LDS conflict-free
             MA(0) MA(1) MA(2) ML(0) MA(3) MA(4) MA(5) ML(1)
+        } else if (OP == 31) {  // alternating FFMA2(U,U) / FFMA(U,U)
+            MA(0) MG(0) MA(1) MG(1) MA(2) MG(2) MA(3) MG(3)
+        } else if (OP == 32) {  // grouped 4 FFMA2 then 4 FFMA
+            MA(0) MA(1) MA(2) MA(3) MG(0) MG(1) MG(2) MG(3)
+        } else if (OP == 33) {  // grouped 8 FFMA2 then 8 FFMA (16 instr per rep)
+            MA(0) MA(1) MA(2) MA(3) MA(4) MA(5) MA(6) MA(7) MG(0) MG(1) MG(2) MG(3) MG(4) MG(5) MG(6) MG(7)
+        } else if (OP == 34) {  // 6 FFMA2 + 2 FFMA
+            MA(0) MA(1) MA(2) MG(0) MA(3) MA(4) MA(5) MG(1)
+        } else if (OP == 35) {  // 2 FFMA2 + 6 FFMA
+            MA(0) MG(0) MG(1) MG(2) MA(1) MG(3) MG(4) MG(5)
         } else if (OP == 25) {  // mix: 4 IMAD(U) + 4 IADD3
             MF(0) MH(4) MF(1) MH(5) MF(2) MH(6) MF(3) MH(7)
         }
@@ -204,6 +214,11 @@ int main() {
     run<20>("mix 4 FFMA(U,U) + 4 PRMT");
     run<21>("mix 2 FFMA2 + 2 PRMT + 2 IADD3 + 2 FFMA2ch");
     run<25>("mix 4 IMAD(U) + 4 IADD3");
+    run<31>("alt 4 FFMA2 + 4 FFMA (12 units)");
+    run<32>("grp 4 FFMA2 + 4 FFMA (12 units)");
+    run<33>("grp 8 FFMA2 + 8 FFMA (24 units; x2 instr)");
+    run<34>("6 FFMA2 + 2 FFMA (14 units)");
+    run<35>("2 FFMA2 + 6 FFMA (10 units)");
     run<26>("FFMA2 R,R64,R64,R64");
     run<27>("mix 4 FFMA2(U,U) + 4 FFMA.SAT");
     run<28>("LDS.32 conflict-free data-dependent");
