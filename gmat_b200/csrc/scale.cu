@@ -147,7 +147,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
         cudaMemcpy(&hy, c->cy[0], sizeof(hy), cudaMemcpyDeviceToHost);
         c->wx[0] = hx.x; c->wx[1] = hx.y; c->wx[2] = hx.z; c->wx[3] = hx.w;
         c->wy[0] = hy.x; c->wy[1] = hy.y; c->wy[2] = hy.z; c->wy[3] = hy.w;
-        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
+        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f && hx.y == .5f && hx.z == .5f && hy.y == .5f && hy.z == .5f;
         c->path = PATH_FUSED2;
     }
     // packed 3-byte rgb -> same format at exactly 2:1: the fused kernel without its colour conversion
@@ -158,7 +158,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
         cudaMemcpy(&hy, c->cy[0], sizeof(hy), cudaMemcpyDeviceToHost);
         c->wx[0] = hx.x; c->wx[1] = hx.y; c->wx[2] = hx.z; c->wx[3] = hx.w;
         c->wy[0] = hy.x; c->wy[1] = hy.y; c->wy[2] = hy.z; c->wy[3] = hy.w;
-        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f;
+        c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f && hx.y == .5f && hx.z == .5f && hy.y == .5f && hy.z == .5f;
         c->path = PATH_FUSED2;
     }
     // bilinear at exactly 2:1 from 8-bit yuv: the integer fast path (scale_bilinear2.cuh)
@@ -209,14 +209,6 @@ static NormK norm_k(int bits) {
 template <int L, int SBITS, int DST>
 static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
 #define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, 16><<<g, 32, 0, st>>>(P)
-    if (L == L_NV12 && SBITS == 8 && DST == D_RGB24 && !wrap) {      // experiment hook: register budget
-        static const int minb = getenv("GMATB_FUSED_MINB") ? atoi(getenv("GMATB_FUSED_MINB")) : 16;
-        if (minb == 20) {
-            if (taps2) fused_csc_scale2_v3_kernel<L_NV12, 8, D_RGB24, true, false, 20><<<g, 32, 0, st>>>(P);
-            else fused_csc_scale2_v3_kernel<L_NV12, 8, D_RGB24, false, false, 20><<<g, 32, 0, st>>>(P);
-            return;
-        }
-    }
     if (wrap) { if (taps2) K(true, true); else K(false, true); }
     else      { if (taps2) K(true, false); else K(false, false); }
 #undef K
@@ -276,17 +268,19 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         Q.m0 = c->M.m[0]; Q.m1 = c->M.m[1]; Q.m3 = c->M.m[3]; Q.m6 = c->M.m[6];
         const int nbatch = src->batch > 1 ? src->batch : 1;
         const int wx = (c->srcW / 8 + 31) / 32;
-        // bands: enough warps for 148 SMs x 24 resident warps a few times over, but no shorter than 8 row pairs
-        int nbl = (int)((148LL * 24 * 3 + (long long)wx * nbatch - 1) / ((long long)wx * nbatch));
+        // bands: ~12 waves of 148 SMs x 24 warps (measured on B200, C2 x 64 frames: 3 waves 1952, 6 -> 2016,
+        // 12 -> 2092, 24 -> 2078 Gpx/s: short bands even out the tail), but no shorter than 8 row pairs
+        static const int blw = getenv("GMATB_BL_WAVES") ? atoi(getenv("GMATB_BL_WAVES")) : 12;
+        int nbl = (int)((148LL * 24 * blw + (long long)wx * nbatch - 1) / ((long long)wx * nbatch));
         nbl = std::max(1, std::min(nbl, (c->dstH + 7) / 8));
         Q.band = (c->dstH + nbl - 1) / nbl;
         nbl = (c->dstH + Q.band - 1) / Q.band;
         dim3 g(wx, nbl, nbatch);
 #define BL(Lx) do { switch (dc) { \
-            case D_RGB24: fused_csc_bilinear2_stream_kernel<Lx, D_RGB24, 24><<<g, 32, 0, c->stream>>>(Q); break; \
-            case D_BGR24: fused_csc_bilinear2_stream_kernel<Lx, D_BGR24, 24><<<g, 32, 0, c->stream>>>(Q); break; \
-            case D_RGBA:  fused_csc_bilinear2_stream_kernel<Lx, D_RGBA, 24><<<g, 32, 0, c->stream>>>(Q); break; \
-            default:      fused_csc_bilinear2_stream_kernel<Lx, D_BGRA, 24><<<g, 32, 0, c->stream>>>(Q); break; } } while (0)
+            case D_RGB24: fused_csc_bilinear2_stream_kernel<Lx, D_RGB24, 32><<<g, 32, 0, c->stream>>>(Q); break; \
+            case D_BGR24: fused_csc_bilinear2_stream_kernel<Lx, D_BGR24, 32><<<g, 32, 0, c->stream>>>(Q); break; \
+            case D_RGBA:  fused_csc_bilinear2_stream_kernel<Lx, D_RGBA, 32><<<g, 32, 0, c->stream>>>(Q); break; \
+            default:      fused_csc_bilinear2_stream_kernel<Lx, D_BGRA, 32><<<g, 32, 0, c->stream>>>(Q); break; } } while (0)
         if (semi) BL(L_NV12); else BL(L_I420);
 #undef BL
         count_launch();
@@ -304,6 +298,7 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     for (int i = 0; i < 4; i++) { P.wx[i] = c->wx[i]; P.wy[i] = c->wy[i]; }
     P.nk = norm_k(bits);
     P.factor = bits == 8 ? 255.f : 65535.f;
+    P.factor_q = P.factor * 0.25f;
     P.dstW = c->dstW; P.dstH = c->dstH;
     const int batch = src->batch > 1 ? src->batch : 1;
     // 4-tap: strips overlap by one lane per side (30 owning lanes per warp); 2-tap: 32
@@ -311,7 +306,8 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     const int warps_x = (c->srcW / 8 + own - 1) / own;
     // enough warps to fill 148 SMs x 16 resident warps a few times over, but bands no
     // shorter than 8 output rows (each band re-converts 2 extra chroma rows)
-    long long want = 148LL * 16 * 4;
+    static const int fwaves = getenv("GMATB_FUSED_WAVES") ? atoi(getenv("GMATB_FUSED_WAVES")) : 8;   // measured: 2 -> 952, 4 -> 975, 8 -> 994, 16 -> 968 Gpx/s
+    long long want = 148LL * 16 * fwaves;
     int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
     static const int min_band = getenv("GMATB_FUSED_MINBAND") ? atoi(getenv("GMATB_FUSED_MINBAND")) : 8;
     nb = std::max(1, std::min(nb, (c->dstH + min_band - 1) / min_band));

@@ -21,7 +21,8 @@
 //   * row-pair registers ping-pong between two explicitly unrolled loop bodies (no copies);
 //   * constants arrive as 8-byte aligned pairs that FFMA2/FMUL2 take straight from uniform
 //     registers.
-// TAPS2 (outer weights exactly zero: default bicubic at 2:1): no halo, 32 owning lanes.
+// TAPS2 (weights exactly {0, .5, .5, 0} on both axes: default bicubic at 2:1): no halo, 32 owning
+// lanes, and each pass is one rounding of a plain sum (see step()).
 #pragma once
 #include "scale_fused.cuh"
 
@@ -34,7 +35,8 @@ struct alignas(8) Fused3Params {
     float m0, m1, m3, m6;   // luma gains of the three rows; m1 == 0 (run-time zero addend, csc_core.cuh)
     float wx[4], wy[4];
     NormK nk;
-    float factor;
+    float factor;      // 255 or 65535
+    float factor_q;    // factor / 4 (exact), TAPS2
     int band;
     int dstW, dstH;
 };
@@ -150,7 +152,9 @@ struct Fused3 {
             for (int c = 0; c < 3; c++) {
                 const f2 p0 = xo == 0 ? PL[c] : C[2 * xo - 1][c];
                 const f2 p3 = xo == 3 ? PR[c] : C[2 * xo + 2][c];
-                const f2 h = hpass<TAPS2>(P.wx, p0, C[2 * xo][c], C[2 * xo + 1][c], p3);
+                // TAPS2: weights are exactly {0, .5, .5, 0}: FFMA(.5, p2, FMUL(.5, p1)) == RN(p1 + p2) / 2 (scaling by a
+                // power of two commutes with rounding), so the halvings are deferred to the final factor
+                const f2 h = TAPS2 ? add2(C[2 * xo][c], C[2 * xo + 1][c]) : hpass<false>(P.wx, p0, C[2 * xo][c], C[2 * xo + 1][c], p3);
                 upk(h, ht[xo][c], hbm[xo][c]);
             }
         if (store) {
@@ -159,8 +163,9 @@ struct Fused3 {
             for (int xo = 0; xo < 4; xo++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
+                    // TAPS2: acc = RN(2h_top + 2h_bottom) = 4 x the reference's vertical result, exactly
                     const float v = TAPS2 ? acc[xo][c] : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
-                    o[xo][c] = trunc_i(__fmul_rn(v, P.factor));
+                    o[xo][c] = trunc_i(__fmul_rn(v, TAPS2 ? P.factor_q : P.factor));
                     if (WRAP) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
                 }
             constexpr bool SW = dst_swap(DST);
@@ -188,8 +193,9 @@ struct Fused3 {
         for (int xo = 0; xo < 4; xo++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
+                if (TAPS2) { acc[xo][c] = __fadd_rn(hbm[xo][c], ht[xo][c]); continue; }
                 float t = __fmul_rn(P.wy[1], ht[xo][c]);
-                if (!TAPS2) t = __fmaf_rn(P.wy[0], hb_prev[xo][c], t);
+                t = __fmaf_rn(P.wy[0], hb_prev[xo][c], t);
                 t = __fmaf_rn(P.wy[2], hbm[xo][c], t);
                 acc[xo][c] = t;
                 hb_prev[xo][c] = hbm[xo][c];
