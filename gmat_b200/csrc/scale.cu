@@ -305,11 +305,12 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     const int own = c->taps2 ? 32 : 30;
     const int warps_x = (c->srcW / 8 + own - 1) / own;
     // enough warps to fill 148 SMs x 16 resident warps a few times over, but bands no
-    // shorter than 8 output rows (each band re-converts 2 extra chroma rows)
+    // shorter than 32 output rows (each band converts 2 extra row pairs to prime its accumulators; measured:
+    // 8 -> 32 rows is +7 % on 4-frame launches, neutral on 64-frame ones)
     static const int fwaves = getenv("GMATB_FUSED_WAVES") ? atoi(getenv("GMATB_FUSED_WAVES")) : 8;   // measured: 2 -> 952, 4 -> 975, 8 -> 994, 16 -> 968 Gpx/s
     long long want = 148LL * 16 * fwaves;
     int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
-    static const int min_band = getenv("GMATB_FUSED_MINBAND") ? atoi(getenv("GMATB_FUSED_MINBAND")) : 8;
+    static const int min_band = getenv("GMATB_FUSED_MINBAND") ? atoi(getenv("GMATB_FUSED_MINBAND")) : 32;
     nb = std::max(1, std::min(nb, (c->dstH + min_band - 1) / min_band));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;

@@ -289,22 +289,27 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
         const Row t = A; A = B; B = t;
         k++; pd += pitch_d;
     };
-    slow_trip();
-    // steady state: pairs k+2 and k+3 are interior (no clamps): warp-uniform offsets advance by constant steps
-    {
-        unsigned ot = (unsigned)(2 * k + 4) * pitch_y, ob = ot + pitch_y, oc = (unsigned)(k + 2) * pitch_c, oc2 = (unsigned)(k + 2) * pitch_c2;
-        const unsigned sy = 2 * pitch_y;
-        auto refill = [&](Row &R) { load_at(R, ot, ob, oc, oc2); ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2; };
-        while (k + 3 <= yo_end - 1) {
-            F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i, refill);
-            pd += pitch_d;
-            F::step(P, B, acc, hb_prev, owner, pd, alpha_i, refill);
-            pd += pitch_d;
-            k += 2;
+    // warp-uniform offsets of the pair the steady-state loop loads next (k+2); no clamps there
+    unsigned ot = 0, ob = 0, oc = 0, oc2 = 0;
+    const unsigned sy = 2 * pitch_y;
+    auto refill = [&](Row &R) { load_at(R, ot, ob, oc, oc2); ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2; };
+#pragma unroll 1
+    while (k <= yo_end) {
+        if (k >= yo_begin && k + 3 <= yo_end - 1) {
+            // steady state: pairs k+2 and k+3 are interior, A and B ping-pong
+            ot = (unsigned)(2 * k + 4) * pitch_y; ob = ot + pitch_y; oc = (unsigned)(k + 2) * pitch_c; oc2 = (unsigned)(k + 2) * pitch_c2;
+#pragma unroll 1
+            do {
+                F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i, refill);
+                pd += pitch_d;
+                F::step(P, B, acc, hb_prev, owner, pd, alpha_i, refill);
+                pd += pitch_d;
+                k += 2;
+            } while (k + 3 <= yo_end - 1);
+        } else {
+            slow_trip();         // the first pair and the last three or four of the band (one copy of the code)
         }
     }
-#pragma unroll 1
-    while (k <= yo_end) slow_trip();
 }
 
 template <int L, int SBITS, int DST, bool TAPS2, bool WRAP, int MINB>

@@ -4,7 +4,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import gmat_b200 as g
 from gmat_b200 import FMT, SWS, BORDER, INTERP, FrameBatch, SwsContext
-dev = torch.device("cuda:0"); B = 16
+dev = torch.device("cuda:0"); B = int(os.environ.get("NCU_B", "64"))
 HW = SWS.HWACCEL_CUDA
 src = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); src.buf.random_(0, 256)
 d1080 = FrameBatch(FMT.RGB24, 1920, 1080, B, device=dev)

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import gmat_b200 as g
 from gmat_b200 import FMT, SWS, BORDER, FrameBatch, SwsContext
 dev = torch.device("cuda:0")
-PEAK = 6580.9
+PEAK = 6552.0
 
 def timeit(fn, n=10):
     for _ in range(3): fn()

@@ -2,7 +2,7 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from gmat_b200 import FMT, SWS, FrameBatch, SwsContext
-dev = torch.device("cuda:0"); B = 64
+dev = torch.device("cuda:0"); B = int(os.environ.get("PERF_B", "64"))
 src = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); src.buf.random_(0, 256)
 dst = FrameBatch(FMT.RGB24, 1920, 1080, B, device=dev)
 for label, flag, param in (("A=-0.75", SWS.BICUBIC, (0.75,)), ("A=0", SWS.BICUBIC, None), ("bilinear", SWS.BILINEAR, None)):
