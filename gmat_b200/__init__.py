@@ -18,6 +18,7 @@ from .sws import SwsContext, sws_getContext, sws_scale, sws_freeContext  # noqa:
 from .ops import (  # noqa: F401
     yuv2rgb, rgb2yuv, yuv2yuv, rgb24tobgr24, yuv2rgb_planar_f32,
     crop, flip, rotate, gaussian, median, csc_matrix_yuv2rgb, csc_matrix_rgb2yuv,
+    format_nv12_to_rgbpf32, format_rgbpf32_to_nv12,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -70,6 +70,9 @@ def lib():
         "gmatb_yuv2yuv": (ci, [IP, IP, vp]),
         "gmatb_rgb24tobgr24": (ci, [IP, IP, vp]),
         "gmatb_yuv2rgb_planar_f32": (ci, [IP, IP, ci, cf, C.POINTER(cf), vp]),
+        "gmatb_format_colorspace": (ci, [ci]),
+        "gmatb_format_nv12_to_rgbpf32": (ci, [IP, IP, ci, cf, C.POINTER(cf), ci, vp]),
+        "gmatb_format_rgbpf32_to_nv12": (ci, [IP, IP, ci, vp]),
         "gmatb_sws_create": (vp, [ci, ci, ci, ci, ci, ci, ci, C.POINTER(cd), ci]),
         "gmatb_sws_free": (None, [vp]),
         "gmatb_sws_set_stream": (None, [vp, vp]),

@@ -38,6 +38,21 @@ def yuv2rgb_planar_f32(src, dst, colorspace=SPC.DEFAULT, norm=255.0, shift=(0.0,
     check(lib().gmatb_yuv2rgb_planar_f32(C.byref(s), C.byref(d), colorspace, norm, sh, _st(stream)), "yuv2rgb_planar_f32")
 
 
+def format_nv12_to_rgbpf32(src, dst, av_colorspace=2, norm=255.0, shift=None, bgr_planes=False, stream=None):
+    """format_cuda NV12 -> RGBPF32 (vf_format_cuda.c:193, format_cuda_kernel.cu:583-609); av_colorspace is the
+    frame's AVColorSpace (2 = unspecified -> the filter's BT.709 default)"""
+    s, d = _img(src), _img(dst)
+    sh = None if shift is None else (C.c_float * 3)(*shift)
+    check(lib().gmatb_format_nv12_to_rgbpf32(C.byref(s), C.byref(d), av_colorspace, norm, sh, int(bgr_planes), _st(stream)),
+          "format_nv12_to_rgbpf32")
+
+
+def format_rgbpf32_to_nv12(src, dst, av_colorspace=2, stream=None):
+    """format_cuda RGBPF32 -> NV12 (vf_format_cuda.c:198, format_cuda_kernel.cu:625-631)"""
+    s, d = _img(src), _img(dst)
+    check(lib().gmatb_format_rgbpf32_to_nv12(C.byref(s), C.byref(d), av_colorspace, _st(stream)), "format_rgbpf32_to_nv12")
+
+
 def rgb2yuv(src, dst, colorspace=SPC.DEFAULT, stream=None):
     s, d = _img(src), _img(dst)
     check(lib().gmatb_rgb2yuv(C.byref(s), C.byref(d), colorspace, _st(stream)), "rgb2yuv")

@@ -22,6 +22,7 @@
  *   gmatb_rotate   -> libavfilter/vf_rotate_nvcv.c:275 (cvcudaRotateSubmit)
  *   gmatb_gaussian -> libavfilter/vf_smooth_nvcv.c:290 (cvcudaGaussianSubmit)
  *   gmatb_median   -> libavfilter/vf_smooth_nvcv.c:294 (cvcudaMedianBlurSubmit)
+ *   gmatb_format_* -> libavfilter/format_cuda_kernel.cu:583-632 (format_cuda filter)
  * The nine libswscale-internal symbols built on top of this layer are declared
  * in gmat_b200_sws.h.
  */
@@ -141,6 +142,21 @@ int gmatb_rgb24tobgr24(const GmatbImage *src, const GmatbImage *dst, void *strea
  * (yuv2rgb_cuda.cu:381-389; the reference launches it with norm=255, shift=0) */
 int gmatb_yuv2rgb_planar_f32(const GmatbImage *src, const GmatbImage *dst, int colorspace,
                              float norm, const float shift_rgb[3], void *stream);
+
+/* ---- format_cuda filter kernels -------------------------------
+ * Replace libavfilter/format_cuda_kernel.cu:583-632 as called by vf_format_cuda.c:185-203.
+ * `av_colorspace` is the frame's enum AVColorSpace; the filter's own matrix selection
+ * (GetConstants, format_cuda_kernel.cu:32-63: BT.709 is the DEFAULT branch, BT470BG = BT.601,
+ * SMPTE170M falls into the default) is applied by gmatb_format_colorspace.
+ *   nv12_to_rgbpf32: planes 0,1,2 = R,G,B (or B,G,R when bgr_planes), float (c - shift[c]) / norm
+ *                    with c the truncated 8-bit result; nv12_to_rgbpf32 = norm 255, shift NULL;
+ *                    nv12_to_rgbpf32_shift / nv12_to_bgrpf32_shift = the general form.
+ *   rgbpf32_to_nv12: planar float in [0,1] x 255 -> NV12, 2x2 float mean chroma; width % 4 == 0,
+ *                    height even, planes 16-byte aligned. */
+int gmatb_format_colorspace(int av_colorspace);
+int gmatb_format_nv12_to_rgbpf32(const GmatbImage *src, const GmatbImage *dst, int av_colorspace,
+                                 float norm, const float shift_rgb[3], int bgr_planes, void *stream);
+int gmatb_format_rgbpf32_to_nv12(const GmatbImage *src, const GmatbImage *dst, int av_colorspace, void *stream);
 
 /* ---- scaling context (mirror of SwsContext's CUDA path) -------------------- */
 typedef struct GmatbSws GmatbSws;

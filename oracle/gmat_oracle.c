@@ -23,6 +23,10 @@
  *        vf_smooth_nvcv.c:290,294.  PARITY UNPINNED: no source, no binary, no reference
  *        test pins them; this file is the specification (SURVEY.md 8c P-FILTERS).
  *   crop / flip        -- exact copies (vf_crop_nvcv.c:277, vf_flip_nvcv.c:251).
+ *   format_cuda        -- ffmpeg-gpu/libavfilter/format_cuda_kernel.cu:32-96 (matrix selection),
+ *        :257-297 (NV12 -> planar float), :516-570 (planar float -> NV12), SASS order.  PINNED:
+ *        golden vectors produced by that file compiled unmodified (oracle O3 =
+ *        oracle/_ref/libref_format_cuda.so) on a B200, tests/golden/make_golden_format.py.
  */
 #include <math.h>
 #include <stdint.h>
@@ -673,5 +677,61 @@ int orc_median(const GmatbImage *s, const GmatbImage *d, int kw, int kh)
                     ((uint8_t *)plane(d, 0, f))[(size_t)y * d->linesize[0] + (size_t)x * bpp + c] = win[N / 2];
                 }
     }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- format_cuda */
+/* GetConstants (format_cuda_kernel.cu:32-63): the colourspace whose matrix the filter uploads */
+int orc_format_colorspace(int av_colorspace)
+{
+    switch (av_colorspace) {
+    case GMATB_SPC_FCC: case GMATB_SPC_BT470BG: case GMATB_SPC_SMPTE240M: return av_colorspace;
+    case GMATB_SPC_BT2020_NCL: case GMATB_SPC_BT2020_CL: return GMATB_SPC_BT2020_NCL;
+    default: return GMATB_SPC_BT709;      /* BT709, SMPTE170M, unspecified, ... */
+    }
+}
+
+/* float -> uint8_t as nvcc compiles it there: F2I.U32.TRUNC (negative -> 0) then the low byte */
+static unsigned trunc_u8_wrap(float v)
+{
+    if (!(v > 0.0f)) return 0;
+    if (v >= 4294967296.0f) return 255;     /* F2I.U32 saturates at 0xFFFFFFFF */
+    return (unsigned)v & 0xFFu;
+}
+
+/* RgbpToYuvKernel<uchar2, RGBAF32, float2> (format_cuda_kernel.cu:516-570).  m = matRgb2Yuv.
+ * Even width and height (the reference returns early for the last odd column/row). */
+int orc_format_rgbpf32_to_nv12(const GmatbImage *s, const GmatbImage *d, const float m[9])
+{
+    const int nb = s->batch > 1 ? s->batch : 1;
+    if ((s->width | s->height) & 1) return -1;
+    for (int f = 0; f < nb; f++)
+        for (int y = 0; y < s->height; y += 2)
+            for (int x = 0; x < s->width; x += 2) {
+                float raw[3][2][2], v[3][2][2];
+                for (int c = 0; c < 3; c++)
+                    for (int r = 0; r < 2; r++)
+                        for (int h = 0; h < 2; h++) {
+                            raw[c][r][h] = ((const float *)(plane(s, c, f) + (size_t)(y + r) * s->linesize[c]))[x + h];
+                            v[c][r][h] = raw[c][r][h] * 255.0f;
+                        }
+                uint8_t *py = (uint8_t *)plane(d, 0, f) + (size_t)y * d->linesize[0] + x;
+                for (int r = 0; r < 2; r++)
+                    for (int h = 0; h < 2; h++) {
+                        const float b = (r == 1 && h == 1) ? v[1][1][1] : v[2][r][h];      /* :560 passes g for b */
+                        float t = v[1][r][h] * m[1];
+                        t = fmaf(v[0][r][h], m[0], t);
+                        t = fmaf(b, m[2], t);
+                        py[(size_t)r * d->linesize[0] + h] = (uint8_t)trunc_u8_wrap(t + 16.0f);
+                    }
+                const float rm = (((v[0][0][0] + v[0][0][1]) + v[0][1][0]) + v[0][1][1]) * 0.25f;
+                const float gm = (((v[1][0][0] + v[1][0][1]) + v[1][1][0]) + v[1][1][1]) * 0.25f;
+                const float bm = fmaf(raw[2][1][1], 255.0f, (v[2][0][0] + v[2][0][1]) + v[2][1][0]) * 0.25f;   /* contracted by nvcc */
+                float u = gm * m[4]; u = fmaf(rm, m[3], u); u = fmaf(bm, m[5], u);
+                float w = gm * m[7]; w = fmaf(rm, m[6], w); w = fmaf(bm, m[8], w);
+                uint8_t *pc = (uint8_t *)plane(d, 1, f) + (size_t)(y >> 1) * d->linesize[1] + x;
+                pc[0] = (uint8_t)trunc_u8_wrap(u + 128.0f);
+                pc[1] = (uint8_t)trunc_u8_wrap(w + 128.0f);
+            }
     return 0;
 }

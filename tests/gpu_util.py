@@ -68,6 +68,35 @@ def o2():
     return _o2
 
 
+_o3 = None
+
+
+def o3():
+    """the reference's format_cuda kernels (libavfilter/format_cuda_kernel.cu), compiled unmodified for sm_100a"""
+    global _o3
+    if _o3 is None:
+        L = C.CDLL(os.path.join(REF, "libref_format_cuda.so"))
+        pp, pi = C.POINTER(vp), C.POINTER(ci)
+        L.nv12_to_rgbpf32.argtypes = [vp, pp, pi, pp, pi, ci, ci, ci]
+        L.nv12_to_rgbpf32_shift.argtypes = [vp, pp, pi, pp, pi, ci, ci, C.c_float, C.POINTER(C.c_float), ci]
+        L.nv12_to_bgrpf32_shift.argtypes = [vp, pp, pi, pp, pi, ci, ci, C.c_float, C.POINTER(C.c_float), ci]
+        L.rgbpf32_to_nv12.argtypes = [vp, pp, pi, pp, pi, ci, ci, ci]
+        _o3 = L
+    return _o3
+
+
+def o3_run(kind, src, dst, av_cs=2, norm=255.0, shift=None):
+    L = o3()
+    sp, ss = arrs(src.image()); dp, ds = arrs(dst.image())
+    if kind == "nv12_to_rgbpf32":
+        L.nv12_to_rgbpf32(None, sp, ss, dp, ds, src.w, src.h, av_cs)
+    elif kind in ("nv12_to_rgbpf32_shift", "nv12_to_bgrpf32_shift"):
+        getattr(L, kind)(None, sp, ss, dp, ds, src.w, src.h, norm, (C.c_float * 3)(*shift), av_cs)
+    else:
+        L.rgbpf32_to_nv12(None, sp, ss, dp, ds, src.w, src.h, av_cs)
+    torch.cuda.synchronize()
+
+
 def arrs(img):
     return (vp * 4)(*[img.data[i] for i in range(4)]), (ci * 4)(*[img.linesize[i] for i in range(4)])
 

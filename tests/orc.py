@@ -38,6 +38,8 @@ def orc():
     L.orc_rotate.argtypes = [IP, IP, cd, cd, cd, ci]
     L.orc_gaussian.argtypes = [IP, IP, ci, ci, cd, cd, ci]
     L.orc_median.argtypes = [IP, IP, ci, ci]
+    L.orc_format_colorspace.argtypes = [ci]
+    L.orc_format_rgbpf32_to_nv12.argtypes = [IP, IP, fp]
     _L = L
     return L
 
@@ -81,3 +83,15 @@ def yuv2rgb_scale(src, dst, tables, cs=0, ra=0, wrap=0):
     (cx, px), (cy, py) = tables
     m = matrix_yuv2rgb(cs); s, d = src.image(), dst.image()
     orc().orc_yuv2rgb_scale(C.byref(s), C.byref(d), fptr(m), fptr(cx), iptr(px), fptr(cy), iptr(py), ra, wrap)
+
+
+def format_nv12_to_rgbpf32(src, dst, av_cs=2, norm=255.0, shift=None):
+    """format_cuda's NV12 -> planar float: libgpuscale's planar chain with format_cuda's matrix selection"""
+    m = matrix_yuv2rgb(orc().orc_format_colorspace(av_cs)); s, d = src.image(), dst.image()
+    sh = None if shift is None else fptr(np.asarray(shift, np.float32))
+    orc().orc_yuv2rgb_planar_f32(C.byref(s), C.byref(d), fptr(m), norm, sh)
+
+
+def format_rgbpf32_to_nv12(src, dst, av_cs=2):
+    m = matrix_rgb2yuv(orc().orc_format_colorspace(av_cs)); s, d = src.image(), dst.image()
+    assert orc().orc_format_rgbpf32_to_nv12(C.byref(s), C.byref(d), fptr(m)) == 0
