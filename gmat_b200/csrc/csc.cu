@@ -231,51 +231,65 @@ __global__ void __launch_bounds__(256, GMATB_Y2R_MINB) yuv2rgb_kernel(Img src, I
     }
 }
 
-// yuv -> planar float rgb with (c - shift)/norm   (yuv2rgb_cuda.cu:381-433)
+// yuv -> planar float rgb with (c - shift)/norm   (yuv2rgb_cuda.cu:381-433; format_cuda_kernel.cu:257-297)
+// c is an integer in 0..255, so the IEEE division has only 3 x 256 possible results: each block computes them
+// once into shared memory (768 __fdiv_rn per 8192 pixels instead of 3 per pixel -- the division expands to
+// ~10 instructions and made this kernel compute-bound at 32 % of the HBM roofline) and every pixel is a
+// byte-indexed lookup of the exact quotient.
 template <int L, bool SPARSE>
 __global__ void __launch_bounds__(256) yuv2rgb_planar_f32_kernel(Img src, Img dst, Mat9 M, float norm,
                                                                   float sr, float sg, float sb, int vec_ok) {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
-    const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
-    if (x0 >= src.w || y0 >= src.h) return;
-    const long long fz = blockIdx.z;
-    const bool full = vec_ok && (x0 + 8 <= src.w) && (y0 + 2 <= src.h);
-    float ym[2][8], um[4], vm[4];
-    load_yuv_tile<L, 8>(src, fz, x0, y0, full, ym, um, vm);
-    constexpr float YB = -(GMATB_MAGIC + 16.f), CB = -(GMATB_MAGIC + 128.f);
-    int r[2][8], g[2][8], b[2][8];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float fu, fv;
-        upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-        ChromaTerms t = chroma_terms<SPARSE, true>(fu, fv, M);     // planar kernels of the reference: FMA form
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
-            csc_pair_i<SPARSE, true>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
-                                     b[rr][2 * j], b[rr][2 * j + 1]);
-        }
+    __shared__ float tab[3][256];
+    {
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        tab[0][t] = __fdiv_rn(__fsub_rn((float)t, sr), norm);
+        tab[1][t] = __fdiv_rn(__fsub_rn((float)t, sg), norm);
+        tab[2][t] = __fdiv_rn(__fsub_rn((float)t, sb), norm);
     }
-    const float sh[3] = {sr, sg, sb};
+    __syncthreads();
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    const int ybase = (blockIdx.y * 8 + threadIdx.y) * 4;          // two row pairs per thread
+    const long long fz = blockIdx.z;
+    if (x0 >= src.w) return;
+#pragma unroll 1
+    for (int rp = 0; rp < 2; rp++) {
+        const int y0 = ybase + 2 * rp;
+        if (y0 >= src.h) return;
+        const bool full = vec_ok && (x0 + 8 <= src.w) && (y0 + 2 <= src.h);
+        float ym[2][8], um[4], vm[4];
+        load_yuv_tile<L, 8>(src, fz, x0, y0, full, ym, um, vm);
+        constexpr float YB = -(GMATB_MAGIC + 16.f), CB = -(GMATB_MAGIC + 128.f);
+        int r[2][8], g[2][8], b[2][8];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        uint8_t *pd = dst.pl[c].p + fz * dst.pl[c].bstride + (size_t)y0 * dst.pl[c].pitch + (size_t)x0 * 4;
+        for (int j = 0; j < 4; j++) {
+            float fu, fv;
+            upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+            ChromaTerms t = chroma_terms<SPARSE, true>(fu, fv, M);     // planar kernels of the reference: FMA form
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                int v = clamp_i(c == 0 ? r[rr][i] : c == 1 ? g[rr][i] : b[rr][i], 255);
-                o[i] = __fdiv_rn(__fsub_rn((float)v, sh[c]), norm);
+            for (int rr = 0; rr < 2; rr++) {
+                f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
+                csc_pair_i<SPARSE, true>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
+                                         b[rr][2 * j], b[rr][2 * j + 1]);
             }
-            float *q = reinterpret_cast<float *>(pd + (size_t)rr * dst.pl[c].pitch);
-            if (full) {
-                __stcs(reinterpret_cast<float4 *>(q), make_float4(o[0], o[1], o[2], o[3]));
-                __stcs(reinterpret_cast<float4 *>(q) + 1, make_float4(o[4], o[5], o[6], o[7]));
-            } else {
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            uint8_t *pd = dst.pl[c].p + fz * dst.pl[c].bstride + (size_t)y0 * dst.pl[c].pitch + (size_t)x0 * 4;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    if (x0 + i < src.w && y0 + rr < src.h) q[i] = o[i];
+                    o[i] = tab[c][clamp_i(c == 0 ? r[rr][i] : c == 1 ? g[rr][i] : b[rr][i], 255)];
+                float *q = reinterpret_cast<float *>(pd + (size_t)rr * dst.pl[c].pitch);
+                if (full) {
+                    __stcs(reinterpret_cast<float4 *>(q), make_float4(o[0], o[1], o[2], o[3]));
+                    __stcs(reinterpret_cast<float4 *>(q) + 1, make_float4(o[4], o[5], o[6], o[7]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (x0 + i < src.w && y0 + rr < src.h) q[i] = o[i];
+                }
             }
         }
     }
@@ -664,7 +678,7 @@ int yuv2rgb_planar_launch(const GmatbImage *src, const GmatbImage *dst, const Ma
     if (!to_img(src, &s, fmt_planes(src->format)) || !to_img(dst, &d, 3)) return GMATB_ERR_INVAL;
     const bool sparse = (M.m[1] == 0.f && M.m[8] == 0.f);
     const int vec = aligned16(s, fmt_planes(src->format)) && aligned16(d, 3);
-    dim3 g = tile_grid(s.w, s.h, 2, src->batch), b(32, 8);
+    dim3 g = tile_grid(s.w, s.h, 4, src->batch), b(32, 8);        // a thread converts 8 columns x 4 rows
     float s0 = shift ? shift[0] : 0.f, s1 = shift ? shift[1] : 0.f, s2 = shift ? shift[2] : 0.f;
     if (src->format == GMATB_FMT_NV12) {
         if (sparse) yuv2rgb_planar_f32_kernel<L_NV12, true><<<g, b, 0, st>>>(s, d, M, norm, s0, s1, s2, vec);
