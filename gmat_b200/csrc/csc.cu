@@ -365,6 +365,78 @@ __host__ __device__ constexpr int srgb_bpp(int s) { return s <= S_BGR24 ? 3 : s 
 __host__ __device__ constexpr bool srgb_swap(int s) { return s == S_BGR24 || s == S_BGRA || s == S_BGRA64; }
 __host__ __device__ constexpr bool srgb_is16(int s) { return s >= S_RGBA64; }
 
+// 8-bit packed rgb -> 8-bit yuv 4:2:0, one full 8x2 tile: the vector path of rgb2yuv_kernel.
+// Same IEEE operations as rgb2y_f / the reference (FADD(FFMA(b,m2,FFMA(r,m0,FMUL(g,m1))),low), integer 2x2
+// mean for chroma), but nothing touches the 16-lane conversion unit: bytes become floats through PRMT magic
+// numbers (2^23 + byte, minus 2^23 is exact), the luma chain runs packed on (top,bottom) pairs, U and V of a
+// block run as one packed pair, the 2x2 mean is exact float arithmetic (sum <= 1020, x 0.25, floor through
+// RZ(q + 2^23)), truncation is the round-toward-zero multiply by 2^-149 and the clamp is the saturating I2IP
+// pack.  (The I2F form ran at 55 % of the HBM roofline, conversion-unit bound.)
+template <int SRC, int L>
+__device__ __forceinline__ void rgb2yuv_tile8(const Img &src, const Img &dst, const Mat9 &M, long long fz, int x0, int y0) {
+    constexpr int BPP = srgb_bpp(SRC);
+    constexpr int NW = 2 * BPP;                       // 32-bit words per 8-pixel row
+    uint32_t w[2][NW];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const uint8_t *row = src.pl[0].p + fz * src.pl[0].bstride + (size_t)(y0 + rr) * src.pl[0].pitch + (size_t)x0 * BPP;
+        if (BPP == 4) {
+            const uint4 a = ldg128(row), b = ldg128(row + 16);
+            w[rr][0] = a.x; w[rr][1] = a.y; w[rr][2] = a.z; w[rr][3] = a.w;
+            w[rr][NW - 4] = b.x; w[rr][NW - 3] = b.y; w[rr][NW - 2] = b.z; w[rr][NW - 1] = b.w;
+        } else {
+            const uint2 a = ldg64(row), b = ldg64(row + 8), c = ldg64(row + 16);
+            w[rr][0] = a.x; w[rr][1] = a.y; w[rr][2] = b.x; w[rr][3] = b.y; w[rr][4] = c.x; w[rr][5] = c.y;
+        }
+    }
+    const f2 nm = bc(-GMATB_MAGIC), z = bc(GMATB_TWO_M149);
+    f2 c2[3][8];                                      // [component r,g,b][column] = (top, bottom), exact integers as floats
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int bi = i * BPP + k, comp = srgb_swap(SRC) ? 2 - k : k;
+            const float t = __uint_as_float(__byte_perm(w[0][bi >> 2], 0x4B000000u, 0x7440u | (bi & 3)));
+            const float b = __uint_as_float(__byte_perm(w[1][bi >> 2], 0x4B000000u, 0x7440u | (bi & 3)));
+            c2[comp][i] = add2(pk(t, b), nm);
+        }
+    int yt[8], yb[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        f2 t = mul2(c2[1][i], bc(M.m[1]));
+        t = fma2(c2[0][i], bc(M.m[0]), t);
+        t = fma2(c2[2][i], bc(M.m[2]), t);
+        upki(mul2_rz(add2(t, bc(16.0f)), z), yt[i], yb[i]);
+    }
+    uint8_t *pdy = dst.pl[0].p + fz * dst.pl[0].bstride + (size_t)y0 * dst.pl[0].pitch + x0;
+    stg64(pdy, make_uint2(pack4_u8(yt[0], yt[1], yt[2], yt[3]), pack4_u8(yt[4], yt[5], yt[6], yt[7])));
+    stg64(pdy + dst.pl[0].pitch, make_uint2(pack4_u8(yb[0], yb[1], yb[2], yb[3]), pack4_u8(yb[4], yb[5], yb[6], yb[7])));
+    int uu[4], vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float mean[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float st, sb;
+            upk(add2(c2[k][2 * j], c2[k][2 * j + 1]), st, sb);             // row sums, then the block sum: all exact
+            const float q = __fmul_rn(__fadd_rn(st, sb), 0.25f);
+            mean[k] = __fadd_rn(__fadd_rz(q, GMATB_MAGIC), -GMATB_MAGIC);    // (r0+r1+r2+r3)/4 in integers (:685-687)
+        }
+        f2 t = mul2(bc(mean[1]), pk(M.m[4], M.m[7]));
+        t = fma2(bc(mean[0]), pk(M.m[3], M.m[6]), t);
+        t = fma2(bc(mean[2]), pk(M.m[5], M.m[8]), t);
+        upki(mul2_rz(add2(t, bc(128.0f)), z), uu[j], vv[j]);
+    }
+    const int cx = x0 >> 1, cy = y0 >> 1;
+    if (L == L_NV12) {
+        stg64(dst.pl[1].p + fz * dst.pl[1].bstride + (size_t)cy * dst.pl[1].pitch + (size_t)cx * 2,
+              make_uint2(pack4_u8(uu[0], vv[0], uu[1], vv[1]), pack4_u8(uu[2], vv[2], uu[3], vv[3])));
+    } else {
+        stg32(dst.pl[1].p + fz * dst.pl[1].bstride + (size_t)cy * dst.pl[1].pitch + cx, pack4_u8(uu[0], uu[1], uu[2], uu[3]));
+        stg32(dst.pl[2].p + fz * dst.pl[2].bstride + (size_t)cy * dst.pl[2].pitch + cx, pack4_u8(vv[0], vv[1], vv[2], vv[3]));
+    }
+}
+
 // DBITS: 8 (NV12 / YUV420P) or 16 (P016 from 64-bit rgb, yuv2rgb_cuda.cu:741-746).
 // 16-bit rgb -> 8-bit yuv uses the high byte of each component (the reference
 // mis-reads every non-RGB24 source as RGB24, :748-762 -- not reproduced).
@@ -385,6 +457,9 @@ __global__ void __launch_bounds__(256, GMATB_R2Y_MINB) rgb2yuv_kernel(Img src, I
     const uint8_t *ps = src.pl[0].p + fz * src.pl[0].bstride;
 
     const bool full = vec_ok && x0 + 8 <= W && y0 + 2 <= H;
+    if constexpr (!srgb_is16(SRC) && DBITS == 8) {
+        if (full) { rgb2yuv_tile8<SRC, L>(src, dst, M, fz, x0, y0); return; }
+    }
     int cr[2][8], cg[2][8], cb[2][8];
     if (full) {
         // 128/64-bit row loads: 24 / 32 / 64 bytes per 8-pixel row
