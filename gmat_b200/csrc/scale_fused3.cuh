@@ -137,9 +137,14 @@ struct Fused3 {
     static __device__ __forceinline__ void step(const Fused3Params &P, Row &cur, float (&acc)[4][3], float (&hb_prev)[4][3],
                                                 bool store, uint8_t *pd, int alpha_i, Refill refill) {
         f2 C[8][3];
-        const Row now = cur;
-        refill(cur);
-        produce3<L, SBITS>(now, P, C);
+        if (SBITS == 8) {
+            const Row now = cur;
+            refill(cur);
+            produce3<L, SBITS>(now, P, C);
+        } else {             // 16-bit rows are 12 registers each: refill once the raw words are consumed (no third copy)
+            produce3<L, SBITS>(cur, P, C);
+            refill(cur);
+        }
         f2 PL[3] = {0ull, 0ull, 0ull}, PR[3] = {0ull, 0ull, 0ull};
         if (!TAPS2) {
 #pragma unroll
