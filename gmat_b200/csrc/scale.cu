@@ -236,15 +236,6 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
     return set_cuda_error(cudaGetLastError());
 }
 
-static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
-
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
         if (((uintptr_t)a.pl[i].p | (uintptr_t)a.pl[i].pitch | (uintptr_t)a.pl[i].bstride) & (al - 1)) return false;
