@@ -280,6 +280,7 @@ __host__ __device__ inline int border_idx(int i, int n, int mode) {
 
 }  // namespace gmatb
 #include "gauss_stream.cuh"
+#include "median3_stream.cuh"
 #include "rotate_linear.cuh"
 namespace gmatb {
 
@@ -593,6 +594,23 @@ extern "C" int gmatb_median(const GmatbImage *src, const GmatbImage *dst, int kw
     PImg s, d;
     if (!to_pimg(src, &s) || !to_pimg(dst, &d) || !same_geom(s, d) || nbatch(src) != nbatch(dst)) return GMATB_ERR_INVAL;
     if (kw < 1 || kh < 1 || kw > 15 || kh > 15 || kw > s.w || kh > s.h) return GMATB_ERR_INVAL;
+    const int wbytes = d.w * d.bpp;
+    if (kw == 3 && kh == 3 && (wbytes % 16) == 0 && al16(s) && al16(d)) {
+        // streaming u16x2 kernel (median3_stream.cuh): a thread owns 16 byte columns of two row bands
+        Med3Params P;
+        P.sp = s.p; P.dp = d.p; P.spitch = s.pitch; P.dpitch = d.pitch; P.sbs = s.bstride; P.dbs = d.bstride;
+        P.wb = wbytes; P.H = d.h;
+        const int nbt = nbatch(src), gx = (wbytes / 16 + 127) / 128;
+        // rows per band: long bands amortise the two priming rows, but keep ~4 waves of 148 SMs x 4 CTAs
+        int rows = 32;
+        while (rows > 4 && (long long)gx * ((d.h + 2 * rows - 1) / (2 * rows)) * nbt < 148LL * 4 * 4) rows >>= 1;
+        P.rows = rows;
+        dim3 g3(gx, (d.h + 2 * rows - 1) / (2 * rows), nbt);
+        if (d.bpp == 3) median3_stream_kernel<3><<<g3, 128, 0, (cudaStream_t)stream>>>(P);
+        else            median3_stream_kernel<4><<<g3, 128, 0, (cudaStream_t)stream>>>(P);
+        count_launch();
+        return set_cuda_error(cudaGetLastError());
+    }
     if ((kw == 3 && kh == 3) || (kw == 5 && kh == 5)) {
         const size_t sm2 = (size_t)(64 + kw - 1) * (8 + kh - 1) * d.bpp;
         dim3 b2(32, 8), g2((d.w + 63) / 64, (d.h + 7) / 8, nbatch(src));

@@ -109,6 +109,17 @@ def test_median(dev, fmt, w, h):
         assert_same(dd, ref, f"median {kw}x{kh} {w}x{h}")
 
 
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("w,h,n", [(16, 3, 1), (48, 17, 3), (256, 67, 2), (1920, 1080, 2), (3840, 130, 1)])
+def test_median3_stream_kernel(dev, fmt, w, h, n):
+    """the streaming 3x3 kernel (row bytes % 16 == 0): band seams, odd heights, frame edges, batches"""
+    src, ds = pair(fmt, w, h, dev, n)
+    dd = FrameBatch(fmt, w, h, n, device=dev); g.median(ds, dd, 3, 3); torch.cuda.synchronize()
+    ref = FrameBatch(fmt, w, h, n); s, d = src.image(), ref.image()
+    orc.orc().orc_median(C.byref(s), C.byref(d), 3, 3)
+    assert_same(dd, ref, f"median3 stream {w}x{h}x{n}")
+
+
 def test_constant_image_is_a_fixed_point(dev):
     w, h = 1920, 1080
     src = FrameBatch(FMT.RGB24, w, h, 1, device=dev); src.buf.fill_(0)
