@@ -89,20 +89,22 @@ def test_product_does_not_reference_the_oracle():
 
 
 def test_avfilter_glue_compiles_against_reference_headers(tmp_path):
-    """vf_{crop,rotate,flip,smooth,format}_cuda.c are plain C translation units for ffmpeg-gpu's libavfilter;
+    """vf_{crop,rotate,flip,smooth,format,scale}_cuda.c are plain C translation units for ffmpeg-gpu's libavfilter;
     they must compile against the reference's own headers and export `const AVFilter ff_vf_<name>`."""
     ref = "/root/reference/ffmpeg-gpu"
     inc = os.path.join(ROOT, "oracle", "_ref", "include")
     if not (os.path.isdir(ref) and os.path.exists(os.path.join(inc, "config.h"))):
         pytest.skip("reference tree / generated config.h not available here")
     d = os.path.join(ROOT, "gmat_b200", "csrc", "avfilter")
-    for name in ("crop", "rotate", "flip", "smooth", "format"):
+    for name in ("crop", "rotate", "flip", "smooth", "format", "scale"):
         obj = str(tmp_path / f"vf_{name}_cuda.o")
         subprocess.check_call(["gcc", "-c", "-std=c11", "-O1", "-fPIC", "-Wall", "-Werror=implicit-function-declaration",
                                "-DHAVE_AV_CONFIG_H", f"-I{inc}", f"-I{ref}", "-I/usr/local/cuda/include",
                                f"-I{os.path.join(ROOT, 'include')}", os.path.join(d, f"vf_{name}_cuda.c"), "-o", obj])
         syms = subprocess.check_output(["nm", obj]).decode()
         assert f"ff_vf_{name}_cuda" in syms
+        if name == "scale":
+            assert "U gmatb_sws_create" in syms and "U gmatb_sws_scale" in syms and "U ff_scale_eval_dimensions" in syms
         if name == "format":
             assert "U gmatb_format_nv12_to_rgbpf32" in syms and "U gmatb_format_rgbpf32_to_nv12" in syms
         for fn in ("gmatb_crop", "gmatb_rotate", "gmatb_flip", "gmatb_gaussian"):

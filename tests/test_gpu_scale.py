@@ -242,6 +242,24 @@ def test_plane_scaling_vs_reference_nv12_kernels_live(dev):
     assert_same(dd, ref, "nv12->nv12 bicubic vs O2")
 
 
+@pytest.mark.parametrize("fmt", [FMT.YUV420P, FMT.NV12, FMT.P010LE, FMT.P016LE, FMT.RGB0, FMT.BGR0])
+@pytest.mark.parametrize("flag", [SWS.BICUBIC, SWS.LANCZOS, SWS.POINT, SWS.BILINEAR])
+def test_scale_cuda_filter_format_set(dev, fmt, flag):
+    """every (format, algorithm) the scale_cuda glue (csrc/avfilter/vf_scale_cuda.c) can ask for: the context is
+    created, runs, and a constant frame stays constant (each plane keeps its value: all four filters sum to 1)"""
+    sw, sh, dw, dh = 256, 144, 160, 90
+    c = SwsContext(sw, sh, fmt, dw, dh, fmt, flag | HW)
+    src = FrameBatch(fmt, sw, sh, 2, device=dev); src.buf.fill_(0x40)       # every byte 0x40: 8-bit 64, 16-bit 0x4040
+    dd = FrameBatch(fmt, dw, dh, 2, device=dev); dd.buf.fill_(0xEE)
+    c.scale(src, dd); torch.cuda.synchronize()
+    out = dd.payload()
+    if fmt in (FMT.P010LE, FMT.P016LE):
+        v = out.view(np.uint16)
+        assert v.min() >= 0x403F and v.max() <= 0x4040, (int(v.min()), int(v.max()))
+    else:
+        assert out.min() >= 0x3F and out.max() <= 0x40, (int(out.min()), int(out.max()))
+
+
 def test_rgb2yuv_scaled_is_resize_then_convert(dev):
     """swscale_cuda.c:312-341 ordering: resize the rgb source to dst size, then rgb2yuv"""
     sw, sh, dw, dh = 320, 200, 128, 96
