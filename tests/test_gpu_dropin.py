@@ -78,3 +78,41 @@ def test_scaled_through_reference_sws_scale(dev, refsws, flags, param):
 
 def test_unsupported_pair_makes_reference_getcontext_fail(refsws):
     assert not refsws.sws_getContext(64, 48, FMT.RGBPF32LE, 32, 24, FMT.NV12, SWS.HWACCEL_CUDA, None, None, None)
+
+
+def test_reference_metrans_cswscale_caller_unmodified(dev, refsws):
+    """metrans/app/CSwscale.c -- the only in-tree consumer of SWS_HWACCEL_CUDA -- compiled UNMODIFIED
+    (oracle/refbuild target n1) and driven the way metrans/python/swscale.py drives it: Init -> Convert -> Delete on
+    tight NV12 / planar-float buffers.  The result must equal our kernel layer called directly."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_cswscale.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_cswscale.so not built")
+    K = C.CDLL(so)
+    K.SwscaleCuda_Nv12ToRgbpf32_Init.restype = vp
+    K.SwscaleCuda_Nv12ToRgbpf32_Init.argtypes = [ci, ci]
+    K.SwscaleCuda_Nv12ToRgbpf32_Convert.restype = ci
+    K.SwscaleCuda_Nv12ToRgbpf32_Convert.argtypes = [vp, vp, ci, vp, ci, ci, ci, vp]
+    K.SwscaleCuda_Nv12ToRgbpf32_Delete.argtypes = [vp]
+    w, h = 640, 360
+    # tight buffers, as av_image_fill_linesizes / av_image_fill_pointers lay them out
+    rng = np.random.default_rng(3)
+    nv12 = torch.from_numpy(rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)).to(dev)
+    out = torch.zeros(3 * w * h, dtype=torch.float32, device=dev)
+    ctx = K.SwscaleCuda_Nv12ToRgbpf32_Init(w, h)
+    assert ctx
+    st = torch.cuda.Stream()
+    assert K.SwscaleCuda_Nv12ToRgbpf32_Convert(ctx, nv12.data_ptr(), w, out.data_ptr(), 4 * w, w, h, st.cuda_stream) == 0
+    st.synchronize()
+    K.SwscaleCuda_Nv12ToRgbpf32_Delete(ctx)
+    # the same conversion through the kernel layer on the same tight layout
+    exp = torch.zeros_like(out)
+    si = g.GmatbImage(); di = g.GmatbImage()
+    si.data[0] = nv12.data_ptr(); si.data[1] = nv12.data_ptr() + w * h; si.linesize[0] = w; si.linesize[1] = w
+    si.width, si.height, si.format, si.batch = w, h, FMT.NV12, 1
+    for p in range(3):
+        di.data[p] = exp.data_ptr() + 4 * w * h * p; di.linesize[p] = 4 * w
+    di.width, di.height, di.format, di.batch = w, h, FMT.RGBPF32LE, 1
+    g.yuv2rgb(si, di); torch.cuda.synchronize()
+    assert torch.equal(out, exp)
+    v = out.cpu().numpy()
+    assert v.min() >= 0.0 and v.max() <= 1.0 and len(np.unique(v)) > 200
