@@ -24,7 +24,8 @@ def tables(c):
 
 
 @pytest.mark.parametrize("name,flag,param", ALGOS)
-@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 48, 32, 24), (16, 4, 8, 2), (8, 2, 4, 1), (512, 130, 256, 65), (264, 64, 132, 32)])
+@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 48, 32, 24), (16, 4, 8, 2), (8, 2, 4, 1), (512, 130, 256, 65), (264, 64, 132, 32),
+                                         (240, 12, 120, 6), (248, 12, 124, 6), (232, 70, 116, 35), (488, 6, 244, 3)])   # 30 / 31 / 29 / 61 strips: warp seams of the overlapped layout
 @pytest.mark.parametrize("sfmt,dfmt", [(FMT.NV12, FMT.RGB24), (FMT.YUV420P, FMT.BGRA), (FMT.P010LE, FMT.RGB48LE), (FMT.P016LE, FMT.BGRA64LE)])
 def test_fused_2to1_vs_oracle(dev, name, flag, param, sw, sh, dw, dh, sfmt, dfmt):
     src = FrameBatch(sfmt, sw, sh, 2); src.fill_lcg(seed=sw + dh)
