@@ -74,3 +74,21 @@ def test_filter_argument_errors_are_negative_codes():
     with pytest.raises(g.GmatbError):
         g.rotate(nv, nv)                            # filters take packed rgb only (vf_rotate_nvcv.c:92-101)
     assert L.gmatb_launch_count() >= 0
+
+
+def test_format_cuda_argument_errors_and_colourspace_map():
+    """format_cuda entry points (include/gmat_b200.h): argument checks happen before any CUDA call"""
+    L = g.lib()
+    # GetConstants (format_cuda_kernel.cu:32-63): BT.709 is the default branch, SMPTE170M falls into it
+    assert [L.gmatb_format_colorspace(c) for c in (0, 1, 2, 4, 5, 6, 7, 9, 10)] == [1, 1, 1, 4, 5, 1, 7, 9, 9]
+    f = FrameBatch(FMT.RGBPF32LE, 64, 48, 1); n = FrameBatch(FMT.NV12, 64, 48, 1)
+    with pytest.raises(g.GmatbError):
+        g.format_rgbpf32_to_nv12(n, n)                                   # source must be planar float
+    with pytest.raises(g.GmatbError):
+        g.format_rgbpf32_to_nv12(f, FrameBatch(FMT.NV12, 32, 48, 1))     # geometry mismatch
+    with pytest.raises(g.GmatbError):
+        g.format_rgbpf32_to_nv12(FrameBatch(FMT.RGBPF32LE, 66, 48, 1), FrameBatch(FMT.NV12, 66, 48, 1))   # width % 4
+    with pytest.raises(g.GmatbError):
+        g.format_nv12_to_rgbpf32(f, f)                                   # source must be NV12
+    with pytest.raises(g.GmatbError):
+        g.median(FrameBatch(FMT.RGB24, 64, 48, 1), FrameBatch(FMT.RGB24, 64, 48, 1), 3, 49)   # window taller than the frame
