@@ -168,8 +168,9 @@ struct Fused3 {
             for (int xo = 0; xo < 4; xo++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    // TAPS2: acc = RN(2h_top + 2h_bottom) = 4 x the reference's vertical result, exactly
-                    const float v = TAPS2 ? acc[xo][c] : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
+                    // TAPS2: the output row taps only this pair: RN(2h_top + 2h_bottom) = 4 x the reference's vertical
+                    // result, exactly, written in the same step (pd addresses row k)
+                    const float v = TAPS2 ? __fadd_rn(hbm[xo][c], ht[xo][c]) : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
                     o[xo][c] = trunc_i(__fmul_rn(v, TAPS2 ? P.factor_q : P.factor));
                     if (WRAP) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
                 }
@@ -198,7 +199,7 @@ struct Fused3 {
         for (int xo = 0; xo < 4; xo++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                if (TAPS2) { acc[xo][c] = __fadd_rn(hbm[xo][c], ht[xo][c]); continue; }
+                if (TAPS2) continue;
                 float t = __fmul_rn(P.wy[1], ht[xo][c]);
                 t = __fmaf_rn(P.wy[0], hb_prev[xo][c], t);
                 t = __fmaf_rn(P.wy[2], hbm[xo][c], t);
@@ -234,8 +235,12 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
         pv = P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)sl * (4 * SB);
     }
     const unsigned pitch_y = P.src.pl[0].pitch, pitch_c = P.src.pl[1].pitch, pitch_c2 = P.src.pl[2].pitch;
-    // pd addresses output row k-1 while pair k is processed (never dereferenced before row yo_begin)
-    uint8_t *pd = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + ((long long)yo_begin - 2) * (long long)P.dst.pl[0].pitch
+    // 4-tap: pair k finishes output row k-1 and starts row k: pairs yo_begin-1 .. yo_end are consumed, the first two only
+    // prime the accumulators, pd addresses row k-1 while pair k is processed (never dereferenced before row yo_begin).
+    // TAPS2: output row k taps pair k only: pairs yo_begin .. yo_end-1, pd addresses row k.
+    const int kfirst = TAPS2 ? yo_begin : yo_begin - 1, klast = TAPS2 ? yo_end - 1 : yo_end;
+    const int kstore = TAPS2 ? kfirst : kfirst + 2;          // first pair whose step writes a row
+    uint8_t *pd = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + ((long long)kfirst - (TAPS2 ? 0 : 1)) * (long long)P.dst.pl[0].pitch
                 + (long long)(owner ? strip : 0) * (4 * dst_bpp(DST));
     const unsigned pitch_d = P.dst.pl[0].pitch;
     const bool lrep = EDGE && strip < 0, rrep = EDGE && strip >= nstrips;
@@ -280,17 +285,15 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
         alpha_i = trunc_i(__fmul_rn(av, P.factor));
     }
 
-    // Row pair k finishes output row k-1 (written at pd) and starts row k; pairs yo_begin-1 .. yo_end
-    // are consumed, the first two only prime the accumulators.  A holds pair k, B pair k+1; each step
-    // refills its own buffer with the pair two steps ahead.
+    // A holds pair k, B pair k+1; each step refills its own buffer with the pair two steps ahead.
     Row A, B;
-    int k = yo_begin - 1;
+    int k = kfirst;
     load_clamped(k, A);
     load_clamped(k + 1, B);
     // generic trip (rolled; the first pair and the last few of the band): clamped rows, buffers swapped by copy
     auto slow_trip = [&]() {
-        F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i,
-                [&](Row &R) { if (k + 2 <= yo_end) load_clamped(k + 2, R); });
+        F::step(P, A, acc, hb_prev, owner && k >= kstore, pd, alpha_i,
+                [&](Row &R) { if (k + 2 <= klast) load_clamped(k + 2, R); });
         const Row t = A; A = B; B = t;
         k++; pd += pitch_d;
     };
@@ -299,18 +302,18 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
     const unsigned sy = 2 * pitch_y;
     auto refill = [&](Row &R) { load_at(R, ot, ob, oc, oc2); ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2; };
 #pragma unroll 1
-    while (k <= yo_end) {
-        if (k >= yo_begin && k + 3 <= yo_end - 1) {
+    while (k <= klast) {
+        if (k >= yo_begin && k + 3 <= min(klast, HC - 1)) {
             // steady state: pairs k+2 and k+3 are interior, A and B ping-pong
             ot = (unsigned)(2 * k + 4) * pitch_y; ob = ot + pitch_y; oc = (unsigned)(k + 2) * pitch_c; oc2 = (unsigned)(k + 2) * pitch_c2;
 #pragma unroll 1
             do {
-                F::step(P, A, acc, hb_prev, owner && k > yo_begin, pd, alpha_i, refill);
+                F::step(P, A, acc, hb_prev, owner && k >= kstore, pd, alpha_i, refill);
                 pd += pitch_d;
                 F::step(P, B, acc, hb_prev, owner, pd, alpha_i, refill);
                 pd += pitch_d;
                 k += 2;
-            } while (k + 3 <= yo_end - 1);
+            } while (k + 3 <= min(klast, HC - 1));
         } else {
             slow_trip();         // the first pair and the last three or four of the band (one copy of the code)
         }
