@@ -205,7 +205,8 @@ static NormK norm_k(int bits) {
 
 // MINB = resident warps per SM the register allocation must allow (__launch_bounds__(32, MINB)):
 // 16 -> 128 registers, the v3 kernel needs ~120 to keep every constant and both row-pair buffers
-// resident (at 96 it spills and rematerialises parameters inside the loop).
+// resident (at 96 it spills and rematerialises parameters inside the loop).  The 2-tap instantiation fits 80
+// registers, but 16 / 20 / 24 resident warps all measure 1.50-1.54 Tpx/s: it is fma-pipe bound, not latency bound.
 template <int L, int SBITS, int DST>
 static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
 #define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, 16><<<g, 32, 0, st>>>(P)
