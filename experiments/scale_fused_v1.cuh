@@ -8,6 +8,100 @@
 
 namespace gmatb {
 
+// ---- v1-only helpers (moved here from scale_fused.cuh together with the kernel) ----
+struct Fused2Params {
+    Img src, dst;
+    Mat9 M;
+    float wx[4], wy[4];
+    NormK nk;
+    float factor;      // 255 or 65535
+    int band;          // output rows per band
+    int wrap;          // GMATB_SWS_PARITY_WRAP
+    int dstW, dstH;
+};
+
+
+template <int L>
+__device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRow<8> &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const int rc = min(max(k, 0), (H >> 1) - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+    R.yt = ldg64(py + (size_t)rt * P.src.pl[0].pitch + xs);
+    R.yb = ldg64(py + (size_t)rb * P.src.pl[0].pitch + xs);
+    if (L == L_NV12) {
+        R.c0 = ldg64(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs);
+    } else {
+        R.c0.x = ldg32(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + (xs >> 1));
+        R.c0.y = ldg32(P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + (xs >> 1));
+    }
+}
+template <int L>
+__device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRow<16> &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const int rc = min(max(k, 0), (H >> 1) - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride;
+    R.yt = ldg128(py + (size_t)rt * P.src.pl[0].pitch + xs * 2);
+    R.yb = ldg128(py + (size_t)rb * P.src.pl[0].pitch + xs * 2);
+    if (L == L_NV12) {
+        R.c0 = ldg128(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs * 2);
+    } else {
+        uint2 u = ldg64(P.src.pl[1].p + fz * P.src.pl[1].bstride + (size_t)rc * P.src.pl[1].pitch + xs);
+        uint2 v = ldg64(P.src.pl[2].p + fz * P.src.pl[2].bstride + (size_t)rc * P.src.pl[2].pitch + xs);
+        R.c0 = make_uint4(u.x, u.y, v.x, v.y);
+    }
+}
+
+
+__device__ __forceinline__ void fused_load_rgb(const Fused2Params &P, long long fz, int xs, int k, RawRowRGB &R) {
+    const int H = P.src.h;
+    const int rt = min(max(2 * k, 0), H - 1), rb = min(max(2 * k + 1, 0), H - 1);
+    const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)xs * 3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        R.t[i] = ldg64(py + (size_t)rt * P.src.pl[0].pitch + 8 * i);
+        R.b[i] = ldg64(py + (size_t)rb * P.src.pl[0].pitch + 8 * i);
+    }
+}
+template <int L, int SBITS> struct RowSel { typedef RawRow<SBITS> type; };
+template <> struct RowSel<L_RGB3, 8> { typedef RawRowRGB type; };
+template <int L> __device__ __forceinline__ void fused_load(const Fused2Params &P, long long fz, int xs, int k, RawRowRGB &R) {
+    fused_load_rgb(P, fz, xs, k, R);
+}
+
+// one source column (top,bottom) -> normalised (r,g,b) pairs
+template <int SBITS, bool SPARSE>
+__device__ __forceinline__ void fused_column(float ytm, float ybm, const ChromaTerms &t, const Fused2Params &P, f2 (&out)[3]) {
+    constexpr float YB = -(GMATB_MAGIC + (SBITS == 8 ? 16.f : 4096.f));
+    f2 r, g, b;
+    csc_pair_f<SPARSE, SBITS == 16>(add2(pk(ytm, ybm), bc(YB)), t, P.M, r, g, b);
+    out[0] = quant_norm2(r, P.nk); out[1] = quant_norm2(g, P.nk); out[2] = quant_norm2(b, P.nk);
+}
+
+
+// the 8 (top,bottom) column pairs of one iteration as normalised samples
+template <int L, int SBITS, bool SPARSE, typename Row>
+__device__ __forceinline__ void fused_produce(const Row &cur, const Fused2Params &P, f2 (&C)[8][3]) {
+    constexpr float CB = -(GMATB_MAGIC + (SBITS == 8 ? 128.f : 32768.f));
+    float yt[8], yb[8], um[4], vm[4];
+    fused_unpack<L>(cur, yt, yb, um, vm);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float fu, fv;
+        upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+        ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, P.M);
+        fused_column<SBITS, SPARSE>(yt[2 * j], yb[2 * j], t, P, C[2 * j]);
+        fused_column<SBITS, SPARSE>(yt[2 * j + 1], yb[2 * j + 1], t, P, C[2 * j + 1]);
+    }
+}
+template <int L, int SBITS, bool SPARSE>
+__device__ __forceinline__ void fused_produce(const RawRowRGB &cur, const Fused2Params &P, f2 (&C)[8][3]) {
+    rgb_column<0>(cur, P.nk, C[0]); rgb_column<1>(cur, P.nk, C[1]); rgb_column<2>(cur, P.nk, C[2]); rgb_column<3>(cur, P.nk, C[3]);
+    rgb_column<4>(cur, P.nk, C[4]); rgb_column<5>(cur, P.nk, C[5]); rgb_column<6>(cur, P.nk, C[6]); rgb_column<7>(cur, P.nk, C[7]);
+}
+
+
 // raw samples of the one halo column a warp's outer lanes fetch themselves (prefetched one
 // iteration ahead like the strip itself: the consumer must not wait on an L2 round trip).
 //   8-bit yuv : w0 = top luma | bottom luma << 8 | U << 16 | V << 24
