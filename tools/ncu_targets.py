@@ -12,6 +12,12 @@ d720 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
 which = sys.argv[1:] or ["fused", "bilinear", "generic", "rotate", "gauss", "median", "rgb2yuv", "fliph"]
 if "fused" in which:
     SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | HW, (0.75,)).scale(src, d1080)
+if "fused_default" in which:
+    SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | HW).scale(src, d1080)
+if "c3" in which:
+    s8 = FrameBatch(FMT.P010LE, 7680, 4320, 16, device=dev); s8.buf.random_(0, 256); s8.buf[0::2] &= 0xC0
+    d8 = FrameBatch(FMT.RGB48LE, 3840, 2160, 16, device=dev)
+    SwsContext(7680, 4320, FMT.P010LE, 3840, 2160, FMT.RGB48LE, SWS.LANCZOS | HW).scale(s8, d8)
 if "bilinear" in which:
     SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BILINEAR | HW).scale(src, d1080)
 if "generic" in which:
