@@ -82,7 +82,7 @@ report("flip vertical 4K rgb24", timeit(lambda: g.flip(a, b, 0), 5), Bf * 3840 *
 cr = FrameBatch(FMT.RGB24, 1920, 1080, Bf, device=dev)
 report("crop 4K->1080p centre rgb24", timeit(lambda: g.crop(a, cr, -1, -1), 5), Bf * 1920 * 1080, Bf * 2 * 6220800)
 sc = SwsContext(3840, 2160, FMT.RGB24, 1920, 1080, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA)
-report("scale rgb24 4K->1080p bicubic (generic)", timeit(lambda: sc.scale(a, cr), 3), Bf * 3840 * 2160, Bf * (24883200 + 6220800))
+report("scale rgb24 4K->1080p bicubic (fused rgb path)", timeit(lambda: sc.scale(a, cr), 3), Bf * 3840 * 2160, Bf * (24883200 + 6220800))
 # format_cuda kernels
 fsrc = FrameBatch(FMT.NV12, 3840, 2160, 16, device=dev); fsrc.buf.random_(0, 256)
 fpl = FrameBatch(FMT.RGBPF32LE, 3840, 2160, 16, device=dev)
