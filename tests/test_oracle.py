@@ -215,3 +215,46 @@ def test_oracle_vs_reference_resample_golden(golden):
         assert bad == 0, f"{name}: {bad} of {got.size} bytes differ from the reference scale_cuda output"
         n += 1
     assert n >= 40
+
+
+# ---- exactness arguments the kernels lean on, checked in IEEE binary32 on the CPU -------------------------------
+def test_two_tap_half_weights_identity():
+    """scale_fused3.cuh, TAPS2: with weights exactly {0,.5,.5,0} the reference chain
+         h = FFMA(.5, p2, FMUL(.5, p1));  v = FFMA(.5, h_bottom, FMUL(.5, h_top));  out = trunc(FMUL(v, 255))
+       equals  out = trunc(FMUL(RN(RN(p1+p2) + RN(p3+p4)), 255/4))  (scaling by 2^-k commutes with rounding).
+       p = RN(j/255); all 2^16 horizontal pairs exhaustively, 2^21 random 2x2 blocks, 8- and 16-bit factors."""
+    f = np.float32
+    half = f(0.5)
+    for mx, fac in ((255, f(255.0)), (65535, f(65535.0))):
+        j = np.arange(256, dtype=np.float32) if mx == 255 else np.linspace(0, 65535, 256).round().astype(np.float32)
+        p = (j / f(mx)).astype(np.float32)
+        p1, p2 = np.meshgrid(p, p)
+        h_ref = (half * p2 + half * p1).astype(np.float32)          # both products exact -> one rounding, like the FFMA
+        h_new = ((p1 + p2).astype(np.float32) * half).astype(np.float32)
+        assert np.array_equal(h_ref, h_new)
+        rng = np.random.default_rng(7)
+        q = p[rng.integers(0, 256, (4, 1 << 21))]
+        ht = (half * q[1] + half * q[0]).astype(np.float32); hb = (half * q[3] + half * q[2]).astype(np.float32)
+        v = (half * hb + half * ht).astype(np.float32)
+        ref = np.trunc((v * fac).astype(np.float32))
+        s = ((q[0] + q[1]).astype(np.float32) + (q[2] + q[3]).astype(np.float32)).astype(np.float32)
+        new = np.trunc((s * (fac * f(0.25))).astype(np.float32))
+        assert np.array_equal(ref, new)
+        assert float(fac * f(0.25)) * 4 == float(fac)               # factor / 4 is exact
+
+
+def test_integer_mean_through_float_floor():
+    """csc.cu rgb2yuv_tile8: (a+b+c+d)/4 in integers == RZ(0.25*(a+b+c+d) + 2^23) - 2^23 for every block sum"""
+    s = np.arange(0, 4 * 255 + 1, dtype=np.float32)
+    q = (s * np.float32(0.25)).astype(np.float32)                    # exact: multiples of 0.25
+    m = np.float32(8388608.0)
+    assert np.array_equal(np.floor(q + np.float64(m)).astype(np.float32) - m, (s.astype(np.int64) // 4).astype(np.float32))
+
+
+def test_planar_float_table_is_the_division():
+    """csc.cu yuv2rgb_planar_f32_kernel: the per-block table holds exactly the 3 x 256 possible quotients"""
+    for norm, shift in ((255.0, 0.0), (58.395, 123.675), (1.0, -3.5)):
+        c = np.arange(256, dtype=np.float32)
+        tab = ((c - np.float32(shift)).astype(np.float32) / np.float32(norm)).astype(np.float32)
+        for v in (0, 17, 128, 255):
+            assert tab[v] == np.float32(np.float32(np.float32(v) - np.float32(shift)) / np.float32(norm))
