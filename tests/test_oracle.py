@@ -258,3 +258,18 @@ def test_planar_float_table_is_the_division():
         tab = ((c - np.float32(shift)).astype(np.float32) / np.float32(norm)).astype(np.float32)
         for v in (0, 17, 128, 255):
             assert tab[v] == np.float32(np.float32(np.float32(v) - np.float32(shift)) / np.float32(norm))
+
+
+def test_median3_column_sort_identity():
+    """median3_stream.cuh: median of a 3x3 window = med3(max of column minima, med3 of column medians, min of column
+    maxima), and u16 lanes holding 257*byte order like the bytes"""
+    rng = np.random.default_rng(11)
+    w = rng.integers(0, 256, (200000, 3, 3)).astype(np.int64)        # [window, row, column]
+    w[:5000] = rng.integers(0, 3, (5000, 3, 3))                      # many ties
+    s = np.sort(w, axis=1)                                           # sort every column
+    lo, mid, hi = s[:, 0, :], s[:, 1, :], s[:, 2, :]
+    med3 = lambda a, b, c: np.maximum(np.maximum(np.minimum(a, b), np.minimum(b, c)), np.minimum(a, c))
+    got = med3(lo.max(axis=1), med3(mid[:, 0], mid[:, 1], mid[:, 2]), hi.min(axis=1))
+    assert np.array_equal(got, np.median(w.reshape(-1, 9), axis=1).astype(np.int64))
+    b = np.arange(256)
+    assert np.all(np.diff(b * 257) > 0) and np.all((b * 257) & 0xFF == b) and (255 * 257) < 65536
