@@ -67,7 +67,7 @@ __device__ __forceinline__ float4 lanczos_coeffs_rb(float x) {
 }
 
 // one axis of the filter bank: coeffs[o] (4 taps) and pos[o] = px - 1
-__global__ void filter_table_kernel(int algo, int src_n, int dst_n, float A, float4 *coeffs, int *pos) {
+static __global__ void filter_table_kernel(int algo, int src_n, int dst_n, float A, float4 *coeffs, int *pos) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= dst_n) return;
     const float scale = __fdiv_rn((float)src_n, (float)dst_n);

@@ -74,10 +74,21 @@ struct GmatbSws {
     std::vector<int> hpx[2], hpy[2];
     float wx[4], wy[4];
     bool taps2;
+    int iw;   // 0, or 1..3: both axes have the dyadic weights of the exact-integer kernel (scale_fused4i.cuh)
     // scratch
     void *tmp; size_t tmp_size;
     void *stage_src, *stage_dst; size_t stage_src_size, stage_dst_size;
 };
+
+// (a, b, b, a) / 2^s as exact floats on both axes: the integer kernel's instantiations
+static int dyadic_set(const float *wx, const float *wy) {
+    static const struct { int a, b, s; } sets[3] = {{-3, 19, 5}, {-1, 9, 4}, {-1, 5, 3}};
+    for (int i = 0; i < 3; i++) {
+        const float fa = (float)sets[i].a / (float)(1 << sets[i].s), fb = (float)sets[i].b / (float)(1 << sets[i].s);
+        if (wx[0] == fa && wx[3] == fa && wx[1] == fb && wx[2] == fb && wy[0] == fa && wy[3] == fa && wy[1] == fb && wy[2] == fb) return i + 1;
+    }
+    return 0;
+}
 
 static int build_axis(int algo, int srcN, int dstN, float A, float4 **dc, int **dp, std::vector<int> *hp, cudaStream_t st) {
     if (cudaMalloc(dc, sizeof(float4) * dstN) != cudaSuccess || cudaMalloc(dp, sizeof(int) * dstN) != cudaSuccess)
@@ -148,6 +159,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
         c->wx[0] = hx.x; c->wx[1] = hx.y; c->wx[2] = hx.z; c->wx[3] = hx.w;
         c->wy[0] = hy.x; c->wy[1] = hy.y; c->wy[2] = hy.z; c->wy[3] = hy.w;
         c->taps2 = hx.x == 0.f && hx.w == 0.f && hy.x == 0.f && hy.w == 0.f && hx.y == .5f && hx.z == .5f && hy.y == .5f && hy.z == .5f;
+        c->iw = (fmt_bits(srcFormat) == 8 && dstW <= 8191 && dstH <= 131071) ? dyadic_set(c->wx, c->wy) : 0;
         c->path = PATH_FUSED2;
     }
     // packed 3-byte rgb -> same format at exactly 2:1: the fused kernel without its colour conversion
@@ -237,6 +249,9 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
     return set_cuda_error(cudaGetLastError());
 }
 
+// exact-integer instantiations (8-bit yuv sources, dyadic weights): scale_int.cu
+int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
+
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
         if (((uintptr_t)a.pl[i].p | (uintptr_t)a.pl[i].pitch | (uintptr_t)a.pl[i].bstride) & (al - 1)) return false;
@@ -314,6 +329,8 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         launch_fused_t<L_RGB3, 8, D_RGB24>(c->taps2, wrap, g, c->stream, P);
         count_launch();
         rc = set_cuda_error(cudaGetLastError());
+    } else if (c->iw && !(c->flags & GMATB_SWS_FLOAT_CHAIN)) {
+        rc = fused_int_launch(semi, dc, c->iw, wrap, g, c->stream, P);
     } else if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
     else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, wrap, g, c->stream, P);
     *done = (rc == 0);

@@ -46,6 +46,10 @@ __device__ __forceinline__ f2 norm2_inrange(float mt, float mb, const NormK &k) 
     const f2 hi = fma2(pk(mt, mb), bc(k.c1), bc(k.c0));
     return fma2(hi, bc(k.c2), hi);
 }
+__device__ __forceinline__ float norm_inrange(float m, const NormK &k) {      // one value: m = 2^23 + j
+    const float hi = __fmaf_rn(m, k.c1, k.c0);
+    return __fmaf_rn(hi, k.c2, hi);
+}
 template <int C> __device__ __forceinline__ void rgb_column(const RawRowRGB &R, const NormK &nk, f2 (&out)[3]) {
     out[0] = norm2_inrange(rgb_byte_magic<3 * C>(R.t), rgb_byte_magic<3 * C>(R.b), nk);
     out[1] = norm2_inrange(rgb_byte_magic<3 * C + 1>(R.t), rgb_byte_magic<3 * C + 1>(R.b), nk);

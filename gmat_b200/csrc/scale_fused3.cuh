@@ -210,8 +210,10 @@ struct Fused3 {
 };
 
 // The whole band loop; EDGE = this warp holds an out-of-frame provider strip (first / last warp of a row).
+// (bx, fz) = strip block and frame of this warp, [yo_begin, yo_end) = its output rows (the integer kernel of
+// scale_fused4i.cuh hands the rest of a band over to this loop with its own yo_begin).
 template <int L, int SBITS, int DST, bool TAPS2, bool WRAP, bool EDGE>
-__device__ __forceinline__ void fused3_band(const Fused3Params &P) {
+__device__ __forceinline__ void fused3_band(const Fused3Params &P, const int bx, const long long fz, const int yo_begin, const int yo_end) {
     typedef Fused3<L, SBITS, DST, TAPS2, WRAP> F;
     typedef typename F::Row Row;
     constexpr int OWN = TAPS2 ? 32 : 30;
@@ -219,12 +221,9 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P) {
     constexpr int SPP = L == L_RGB3 ? 3 : SB;          // source bytes per pixel in plane 0
     const int lane = threadIdx.x;
     const int nstrips = P.src.w >> 3;
-    const int strip = blockIdx.x * OWN + lane - (TAPS2 ? 0 : 1);
+    const int strip = bx * OWN + lane - (TAPS2 ? 0 : 1);
     const bool owner = (TAPS2 || (lane >= 1 && lane <= 30)) && strip < nstrips;
     const int sl = min(max(strip, 0), nstrips - 1);
-    const long long fz = blockIdx.z;
-    const int yo_begin = blockIdx.y * P.band;
-    const int yo_end = min(yo_begin + P.band, P.dstH);
     const int H = P.src.h, HC = H >> 1;
 
     const uint8_t *py = P.src.pl[0].p + fz * P.src.pl[0].bstride + (size_t)sl * (8 * SPP);
@@ -324,8 +323,9 @@ template <int L, int SBITS, int DST, bool TAPS2, bool WRAP, int MINB>
 __global__ void __launch_bounds__(32, MINB) fused_csc_scale2_v3_kernel(const Fused3Params P) {
     constexpr int OWN = TAPS2 ? 32 : 30;
     const bool edge_warp = !TAPS2 && (blockIdx.x == 0 || (int)(blockIdx.x + 1) * OWN >= (P.src.w >> 3));
-    if (edge_warp) fused3_band<L, SBITS, DST, TAPS2, WRAP, true>(P);
-    else           fused3_band<L, SBITS, DST, TAPS2, WRAP, false>(P);
+    const int yo_begin = blockIdx.y * P.band, yo_end = min(yo_begin + P.band, P.dstH);
+    if (edge_warp) fused3_band<L, SBITS, DST, TAPS2, WRAP, true>(P, blockIdx.x, blockIdx.z, yo_begin, yo_end);
+    else           fused3_band<L, SBITS, DST, TAPS2, WRAP, false>(P, blockIdx.x, blockIdx.z, yo_begin, yo_end);
 }
 
 }  // namespace gmatb

@@ -90,6 +90,9 @@ extern "C" {
  * scale_cuda kernels' missing upper clamp (values >= 256 wrap modulo 256,
  * vf_scale_cuda.cu:1057-1071 + cvt.rzi) instead of saturating. */
 #define GMATB_SWS_PARITY_WRAP   0x40000000
+/* gmat_b200 extension bit: keep the fused 2:1 kernel on the float chain where the exact-integer form
+ * (dyadic bicubic weights, scale_fused4i.cuh) would apply.  Same output bytes; for A/B tests and timing. */
+#define GMATB_SWS_FLOAT_CHAIN   0x20000000
 
 /* ---- interpolation / border codes of the filter layer (NVCV numbering:
  *      NVCV_INTERP_* / NVCV_BORDER_* as used by vf_rotate_nvcv.c:115-135 and
