@@ -21,8 +21,8 @@ static const AVOption smooth_cuda_options[] = {
         { "default",  "gaussian", 0, AV_OPT_TYPE_CONST, { .i64 = SMOOTH_DEFAULT },  0, 0, .flags = GMATB_FLAGS, "type" },
         { "gaussian", "",         0, AV_OPT_TYPE_CONST, { .i64 = SMOOTH_GAUSSIAN }, 0, 0, .flags = GMATB_FLAGS, "type" },
         { "median",   "",         0, AV_OPT_TYPE_CONST, { .i64 = SMOOTH_MEDIAN },   0, 0, .flags = GMATB_FLAGS, "type" },
-    { "kw", "Kernel width",  OFFSET(kw), AV_OPT_TYPE_INT, { .i64 = 3 }, 1, 31, .flags = GMATB_FLAGS },
-    { "kh", "Kernel height", OFFSET(kh), AV_OPT_TYPE_INT, { .i64 = 3 }, 1, 31, .flags = GMATB_FLAGS },
+    { "kw", "Kernel width",  OFFSET(kw), AV_OPT_TYPE_INT, { .i64 = 3 }, 1, GMATB_GAUSS_MAXK, .flags = GMATB_FLAGS },
+    { "kh", "Kernel height", OFFSET(kh), AV_OPT_TYPE_INT, { .i64 = 3 }, 1, GMATB_GAUSS_MAXK, .flags = GMATB_FLAGS },
     { "border_type", "Border mode", OFFSET(border_type), AV_OPT_TYPE_INT, { .i64 = GMATB_BORDER_CONSTANT }, 0, 4, .flags = GMATB_FLAGS, "border" },
         { "constant",   "", 0, AV_OPT_TYPE_CONST, { .i64 = GMATB_BORDER_CONSTANT },   0, 0, .flags = GMATB_FLAGS, "border" },
         { "replicate",  "", 0, AV_OPT_TYPE_CONST, { .i64 = GMATB_BORDER_REPLICATE },  0, 0, .flags = GMATB_FLAGS, "border" },
@@ -44,8 +44,14 @@ static int smooth_config_props(AVFilterLink *outlink)
         av_log(ctx, AV_LOG_ERROR, "kernel %dx%d larger than the %dx%d frame\n", s->kw, s->kh, inlink->w, inlink->h);
         return AVERROR(EINVAL);
     }
-    if (s->type != SMOOTH_MEDIAN && (!(s->kw & 1) || !(s->kh & 1))) {
-        av_log(ctx, AV_LOG_ERROR, "gaussian kernel sizes must be odd\n");
+    /* fail at graph configuration, not on the first frame: both kernels take odd windows, the median up to
+     * GMATB_MEDIAN_MAXK, the gaussian up to GMATB_GAUSS_MAXK (include/gmat_b200.h) */
+    if (!(s->kw & 1) || !(s->kh & 1)) {
+        av_log(ctx, AV_LOG_ERROR, "kernel sizes must be odd (got %dx%d)\n", s->kw, s->kh);
+        return AVERROR(EINVAL);
+    }
+    if (s->type == SMOOTH_MEDIAN && (s->kw > GMATB_MEDIAN_MAXK || s->kh > GMATB_MEDIAN_MAXK)) {
+        av_log(ctx, AV_LOG_ERROR, "median kernel %dx%d larger than %dx%d\n", s->kw, s->kh, GMATB_MEDIAN_MAXK, GMATB_MEDIAN_MAXK);
         return AVERROR(EINVAL);
     }
     return gmatb_config_output(outlink, &s->base, 0, 0);

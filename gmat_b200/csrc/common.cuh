@@ -109,6 +109,7 @@ struct Mat9 { float m[9]; };
 namespace gmatb {
 int  set_cuda_error(cudaError_t e);
 void count_launch(int n = 1);
+void gmatb_log(const char *msg);
 bool to_img(const GmatbImage *g, Img *out, int nplanes);
 int  fmt_planes(int fmt);
 }

@@ -803,6 +803,35 @@ int rgb2yuv_launch(const GmatbImage *src, const GmatbImage *dst, const Mat9 &M, 
     }
 }
 
+static bool yuv_desc(int fmt, int *layout, int *depth);
+
+// The (source, destination) pairs the launchers above and below accept: gmatb_sws_create refuses the others, as
+// the reference refuses them at sws_getContext time (ff_get_unscaled_swscale_cuda leaves convert_unscaled NULL,
+// swscale_unscaled.c:2014-2054, and sws_init_context_cuda returns EINVAL).  kind: 0 yuv->rgb, 1 rgb->yuv, 2 yuv->yuv.
+bool csc_pair_supported(int kind, int sf, int df) {
+    int l, d;
+    auto rgb_src = [](int f, bool *is16) {
+        *is16 = (f == GMATB_FMT_RGBA64LE || f == GMATB_FMT_BGRA64LE);
+        switch (f) {
+        case GMATB_FMT_RGB24: case GMATB_FMT_BGR24: case GMATB_FMT_RGB0: case GMATB_FMT_RGBA: case GMATB_FMT_BGR0: case GMATB_FMT_BGRA:
+        case GMATB_FMT_RGBA64LE: case GMATB_FMT_BGRA64LE: return true;
+        default: return false;
+        }
+    };
+    if (kind == 0) {
+        if (!yuv_desc(sf, &l, &d)) return false;
+        if (df == GMATB_FMT_RGBPF32LE) return sf == GMATB_FMT_NV12 || sf == GMATB_FMT_YUV420P;   // RGBAPF32LE: no alpha plane writer
+        return dst_code(df) >= 0;
+    }
+    if (kind == 1) {
+        bool is16;
+        if (!rgb_src(sf, &is16)) return false;
+        if (df == GMATB_FMT_NV12 || df == GMATB_FMT_YUV420P) return true;
+        return (df == GMATB_FMT_P010LE || df == GMATB_FMT_P016LE) && is16;
+    }
+    return yuv_desc(sf, &l, &d) && yuv_desc(df, &l, &d);
+}
+
 static bool yuv_desc(int fmt, int *layout, int *depth) {
     switch (fmt) {
     case GMATB_FMT_NV12:        *layout = L_NV12; *depth = 8;  return true;

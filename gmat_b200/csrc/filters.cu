@@ -494,6 +494,10 @@ extern "C" int gmatb_rotate(const GmatbImage *src, const GmatbImage *dst, double
     PImg s, d;
     if (!to_pimg(src, &s) || !to_pimg(dst, &d) || !same_geom(s, d) || nbatch(src) != nbatch(dst)) return GMATB_ERR_INVAL;
     if (interp < GMATB_INTERP_NEAREST || interp > GMATB_INTERP_AREA) return GMATB_ERR_INVAL;
+    if (interp == GMATB_INTERP_AREA) {       // NVCV_INTERP_AREA has no meaning for a same-size rotation; CV-CUDA's choice is not pinned
+        static bool said = false;
+        if (!said) { said = true; gmatb_log("gmat_b200: rotate interp=area runs as linear"); }
+    }
     RotParams R;
     const double rad = angle_deg * 3.14159265358979323846 / 180.0;
     R.c = cos(rad); R.s = sin(rad); R.shx = shift_x; R.shy = shift_y; R.interp = interp;
@@ -572,7 +576,7 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
         S.band = (d.h + bands - 1) / bands;
         bands = (d.h + S.band - 1) / S.band;
         dim3 g2((wx + 127) / 128, bands, nb);
-        static const int minb = getenv("GMATB_GAUSS_MINB") ? atoi(getenv("GMATB_GAUSS_MINB")) : 5;
+        const int minb = 5;
 #define GS(B, KW_, KH_) do { if (minb >= 5) gauss_stream_kernel<B, KW_, KH_, 5><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); \
         else gauss_stream_kernel<B, KW_, KH_, 4><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); } while (0)
 #define GK(B, KW_) do { if (kh == 3) GS(B, KW_, 3); else if (kh == 5) GS(B, KW_, 5); else GS(B, KW_, 7); } while (0)
@@ -593,7 +597,8 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
 extern "C" int gmatb_median(const GmatbImage *src, const GmatbImage *dst, int kw, int kh, void *stream) {
     PImg s, d;
     if (!to_pimg(src, &s) || !to_pimg(dst, &d) || !same_geom(s, d) || nbatch(src) != nbatch(dst)) return GMATB_ERR_INVAL;
-    if (kw < 1 || kh < 1 || kw > 15 || kh > 15 || kw > s.w || kh > s.h) return GMATB_ERR_INVAL;
+    // odd windows up to GMATB_MEDIAN_MAXK (the AVFilter option table advertises the same range)
+    if (kw < 1 || kh < 1 || kw > GMATB_MEDIAN_MAXK || kh > GMATB_MEDIAN_MAXK || !(kw & 1) || !(kh & 1) || kw > s.w || kh > s.h) return GMATB_ERR_INVAL;
     const int wbytes = d.w * d.bpp;
     if (kw == 3 && kh == 3 && (wbytes % 16) == 0 && al16(s) && al16(d)) {
         // streaming u16x2 kernel (median3_stream.cuh): a thread owns 16 byte columns of two row bands

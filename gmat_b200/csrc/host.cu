@@ -2,6 +2,7 @@
 // and the unscaled-converter entry points of include/gmat_b200.h.
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include "common.cuh"
 
@@ -16,6 +17,14 @@ int set_cuda_error(cudaError_t e) {
     return GMATB_ERR_CUDA;
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
+
+// Diagnostics that must not be silent (an option that degrades to another algorithm): stderr by default, or the
+// caller's sink -- the libswscale shim and the AVFilter glue route it to av_log.
+static std::atomic<void (*)(const char *)> g_log{nullptr};
+void gmatb_log(const char *msg) {
+    void (*cb)(const char *) = g_log.load();
+    if (cb) cb(msg); else fprintf(stderr, "%s\n", msg);
+}
 
 int fmt_planes(int fmt) {
     switch (fmt) {
@@ -58,6 +67,8 @@ static void get_constants(int cspace, float *wr, float *wb, int *black, int *whi
 }
 
 }  // namespace gmatb
+
+extern "C" void gmatb_set_log(void (*cb)(const char *)) { gmatb::g_log.store(cb); }
 
 using namespace gmatb;
 

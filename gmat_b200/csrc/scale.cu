@@ -16,6 +16,7 @@ int yuv2rgb_planar_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, 
 int rgb2yuv_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, cudaStream_t);
 int yuv2yuv_launch(const GmatbImage *, const GmatbImage *, cudaStream_t);
 int rgb24swap_launch(const GmatbImage *, const GmatbImage *, cudaStream_t);
+bool csc_pair_supported(int kind, int srcFormat, int dstFormat);
 
 enum { K_YUV2RGB = 0, K_RGB2YUV = 1, K_YUV2YUV = 2, K_RGB2RGB = 3 };
 enum { PATH_UNSCALED = 0, PATH_FUSED2 = 1, PATH_GENERIC = 2 };
@@ -78,6 +79,10 @@ struct GmatbSws {
     // scratch
     void *tmp; size_t tmp_size;
     void *stage_src, *stage_dst; size_t stage_src_size, stage_dst_size;
+    // gmatb_sws_scale_host: copy-in / copy-out streams and the events that link them to `stream`; owned by the
+    // context (one context is driven by one thread at a time, like a CPU SwsContext), created on first use on the
+    // device that is current then
+    struct HostPipe *pipe;
 };
 
 // (a, b, b, a) / 2^s as exact floats on both axes: the integer kernel's instantiations
@@ -89,6 +94,10 @@ static int dyadic_set(const float *wx, const float *wy) {
     }
     return 0;
 }
+
+#define GMATB_PIPE_EVENTS 16
+struct HostPipe;
+static void host_pipe_free(HostPipe *hp);
 
 static int build_axis(int algo, int srcN, int dstN, float A, float4 **dc, int **dp, std::vector<int> *hp, cudaStream_t st) {
     if (cudaMalloc(dc, sizeof(float4) * dstN) != cudaSuccess || cudaMalloc(dp, sizeof(int) * dstN) != cudaSuccess)
@@ -110,6 +119,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
     memset(c, 0, offsetof(GmatbSws, hpx));
     c->tmp = c->stage_src = c->stage_dst = nullptr;
     c->tmp_size = c->stage_src_size = c->stage_dst_size = 0;
+    c->pipe = nullptr;
     c->srcW = srcW; c->srcH = srcH; c->srcFmt = srcFormat; c->dstW = dstW; c->dstH = dstH; c->dstFmt = dstFormat;
     c->flags = flags; c->cspace = colorspace; c->stream = 0;
     c->param[0] = param ? param[0] : GMATB_SWS_PARAM_DEFAULT;
@@ -120,6 +130,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
 
     if (srcW == dstW && srcH == dstH) {   // sws_init_context_cuda: unscaled (utils.c:2048-2055)
         c->path = PATH_UNSCALED;
+        if (c->kind != K_RGB2RGB && !csc_pair_supported(c->kind, srcFormat, dstFormat)) { delete c; return nullptr; }
         if (c->kind == K_RGB2RGB && srcFormat != dstFormat &&
             !((srcFormat == GMATB_FMT_RGB24 && dstFormat == GMATB_FMT_BGR24) ||
               (srcFormat == GMATB_FMT_BGR24 && dstFormat == GMATB_FMT_RGB24))) { delete c; return nullptr; }
@@ -129,15 +140,20 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
     if (fmt_bits(srcFormat) == 32 || fmt_bits(dstFormat) == 32) { delete c; return nullptr; }
     if (c->kind == K_YUV2RGB && (rgb_dst_code(dstFormat) < 0 || fmt_bits(srcFormat) != fmt_bits(dstFormat))) { delete c; return nullptr; }
     if (c->kind == K_RGB2RGB && srcFormat != dstFormat) { delete c; return nullptr; }
-    if (c->kind == K_RGB2YUV && (fmt_bits(srcFormat) != 8 || fmt_bits(dstFormat) != 8)) { delete c; return nullptr; }
+    if (c->kind == K_RGB2YUV && (fmt_bits(srcFormat) != 8 || fmt_bits(dstFormat) != 8 || !csc_pair_supported(K_RGB2YUV, srcFormat, dstFormat))) { delete c; return nullptr; }
     if (c->kind == K_YUV2YUV && ((srcW | srcH | dstW | dstH) & 1)) { delete c; return nullptr; }
 
     // algorithm from the SWS_* bit (the reference intends this mapping, swscale_cuda.c:69-74;
     // its own call site passes the wrong field, :305, and always gets LINEAR)
-    if (flags & GMATB_SWS_BICUBIC) c->algo = RS_BICUBIC;
+    // map_resize_algo tests BILINEAR, then BICUBIC, then AREA (swscale_cuda.c:68-73); LANCZOS / POINT are ours.
+    // SWS_AREA: the reference maps it to NVCV_INTERP_AREA (CV-CUDA, closed); we have no pinned definition of it and
+    // run bilinear -- said once per context on stderr, never silently.
+    if (flags & (GMATB_SWS_BILINEAR | GMATB_SWS_FAST_BILINEAR)) c->algo = RS_BILINEAR;
+    else if (flags & GMATB_SWS_BICUBIC) c->algo = RS_BICUBIC;
+    else if (flags & GMATB_SWS_AREA) { c->algo = RS_BILINEAR; gmatb_log("gmat_b200: SWS_AREA is not implemented, using SWS_BILINEAR"); }
     else if (flags & GMATB_SWS_LANCZOS) c->algo = RS_LANCZOS;
     else if (flags & GMATB_SWS_POINT) c->algo = RS_NEAREST;
-    else c->algo = RS_BILINEAR;   // SWS_BILINEAR, SWS_FAST_BILINEAR, SWS_AREA, nothing: map_resize_algo's fallthrough
+    else c->algo = RS_BILINEAR;   // no scaler bit: map_resize_algo's fallthrough (NVCV_INTERP_LINEAR)
     c->ra = (c->algo == RS_BILINEAR || c->algo == RS_NEAREST);
     const bool pdef = (c->param[0] == GMATB_SWS_PARAM_DEFAULT);
     c->A = pdef ? 0.0f : -(float)c->param[0];   // vf_scale_cuda.cu:972
@@ -186,6 +202,7 @@ extern "C" void gmatb_sws_free(GmatbSws *c) {
         cudaFree(c->cx[i]); cudaFree(c->cy[i]); cudaFree(c->px[i]); cudaFree(c->py[i]);
     }
     cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst);
+    host_pipe_free(c->pipe);
     delete c;
 }
 extern "C" void gmatb_sws_set_stream(GmatbSws *c, void *stream) { if (c) c->stream = (cudaStream_t)stream; }
@@ -277,7 +294,7 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         const int wx = (c->srcW / 8 + 31) / 32;
         // bands: ~12 waves of 148 SMs x 24 warps (measured on B200, C2 x 64 frames: 3 waves 1952, 6 -> 2016,
         // 12 -> 2092, 24 -> 2078 Gpx/s: short bands even out the tail), but no shorter than 8 row pairs
-        static const int blw = getenv("GMATB_BL_WAVES") ? atoi(getenv("GMATB_BL_WAVES")) : 12;
+        const int blw = 12;
         int nbl = (int)((148LL * 24 * blw + (long long)wx * nbatch - 1) / ((long long)wx * nbatch));
         nbl = std::max(1, std::min(nbl, (c->dstH + 7) / 8));
         Q.band = (c->dstH + nbl - 1) / nbl;
@@ -314,10 +331,10 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     // enough warps to fill 148 SMs x 16 resident warps a few times over, but bands no
     // shorter than 32 output rows (each band converts 2 extra row pairs to prime its accumulators; measured:
     // 8 -> 32 rows is +7 % on 4-frame launches, neutral on 64-frame ones)
-    static const int fwaves = getenv("GMATB_FUSED_WAVES") ? atoi(getenv("GMATB_FUSED_WAVES")) : 8;   // measured: 2 -> 952, 4 -> 975, 8 -> 994, 16 -> 968 Gpx/s
+    const int fwaves = 8;   // measured: 2 -> 952, 4 -> 975, 8 -> 994, 16 -> 968 Gpx/s
     long long want = 148LL * 16 * fwaves;
     int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
-    static const int min_band = getenv("GMATB_FUSED_MINBAND") ? atoi(getenv("GMATB_FUSED_MINBAND")) : 32;
+    const int min_band = 32;
     nb = std::max(1, std::min(nb, (c->dstH + min_band - 1) / min_band));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
@@ -329,7 +346,7 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         launch_fused_t<L_RGB3, 8, D_RGB24>(c->taps2, wrap, g, c->stream, P);
         count_launch();
         rc = set_cuda_error(cudaGetLastError());
-    } else if (c->iw && !(c->flags & GMATB_SWS_FLOAT_CHAIN)) {
+    } else if (c->iw && (c->flags & GMATB_SWS_INT_CHAIN)) {
         rc = fused_int_launch(semi, dc, c->iw, wrap, g, c->stream, P);
     } else if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
     else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, wrap, g, c->stream, P);
@@ -359,7 +376,7 @@ static int run_generic(GmatbSws *c, int bank, const Img &s, const Img &d, int dW
         // window: planar ch floats per pixel for 3/4 components (rounded to 16 bytes), else st; horizontal results: st
         smem = (st == 4 ? (((size_t)mw * mh * ch + 3) & ~(size_t)3) : (size_t)mw * mh * st) * sizeof(float) + (size_t)mh * tw * st * sizeof(float);
         P.win_w = mw; P.win_h = mh;
-        static const size_t budget = (getenv("GMATB_GEN_SMEM") ? atoi(getenv("GMATB_GEN_SMEM")) : 64) * 1024;
+        const size_t budget = 64 * 1024;
         if (smem <= budget || (tw == 1 && th == 1)) break;
         if (th > 8) th /= 2; else if (tw >= 2 * th && tw > 8) tw /= 2; else if (th > 1) th /= 2; else tw /= 2;
     }
@@ -578,21 +595,30 @@ extern "C" int gmatb_sws_scale(GmatbSws *c, const uint8_t *const src[4], const i
 // no host-buffer call at all: its callers cudaMemcpy around sws_scale themselves).
 struct HostPipe {
     cudaStream_t in, out;
-    cudaEvent_t ev_in[64], ev_k[64];
+    cudaEvent_t ev_in[GMATB_PIPE_EVENTS], ev_k[GMATB_PIPE_EVENTS];
+    int nev;
     bool ok;
 };
-static HostPipe *host_pipe() {
-    static HostPipe hp;
-    static bool init = false;
-    if (!init) {
-        init = true;
-        hp.ok = cudaStreamCreateWithFlags(&hp.in, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&hp.out, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 64 && hp.ok; i++)
-            hp.ok = cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&hp.ev_k[i], cudaEventDisableTiming) == cudaSuccess;
+static HostPipe *host_pipe(GmatbSws *c) {
+    if (c->pipe) return c->pipe;
+    HostPipe *hp = new HostPipe();
+    hp->in = hp->out = nullptr; hp->nev = 0;
+    hp->ok = cudaStreamCreateWithFlags(&hp->in, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&hp->out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < GMATB_PIPE_EVENTS && hp->ok; i++) {
+        hp->ok = cudaEventCreateWithFlags(&hp->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&hp->ev_k[i], cudaEventDisableTiming) == cudaSuccess;
+        if (hp->ok) hp->nev = i + 1;
     }
-    return &hp;
+    c->pipe = hp;
+    return hp;
+}
+static void host_pipe_free(HostPipe *hp) {
+    if (!hp) return;
+    for (int i = 0; i < hp->nev; i++) { cudaEventDestroy(hp->ev_in[i]); cudaEventDestroy(hp->ev_k[i]); }
+    if (hp->in) cudaStreamDestroy(hp->in);
+    if (hp->out) cudaStreamDestroy(hp->out);
+    delete hp;
 }
 
 extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, const GmatbImage *dst_host) {
@@ -614,7 +640,7 @@ extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, con
         if (s.data[p]) sdev.data[p] = ds + ((uintptr_t)s.data[p] - slo);
         if (d.data[p]) ddev.data[p] = dd + ((uintptr_t)d.data[p] - dlo);
     }
-    HostPipe *hp = host_pipe();
+    HostPipe *hp = host_pipe(c);
     // chunking needs frames that are whole, equally spaced byte ranges (the FrameBatch / frame-pool layout)
     bool chunkable = hp->ok && n > 1;
     const long long sfs = s.batch_stride[0], dfs = d.batch_stride[0];
@@ -632,7 +658,7 @@ extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, con
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         return set_cuda_error(e);
     }
-    int per = (n + 7) / 8;                       // ~8 chunks in flight
+    int per = (n + 7) / 8;                       // ~8 chunks in flight (<= GMATB_PIPE_EVENTS: every chunk has its own events)
     if (per < 1) per = 1;
     const int nchunks = (n + per - 1) / per;
     cudaError_t e = cudaSuccess;
@@ -642,8 +668,8 @@ extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, con
         const size_t so = (size_t)f0 * sfs, sb = (f0 + fn == n) ? (shi - slo) - so : (size_t)fn * sfs;
         const size_t dofs = (size_t)f0 * dfs, db = (f0 + fn == n) ? (dhi - dlo) - dofs : (size_t)fn * dfs;
         e = cudaMemcpyAsync(ds + so, (const uint8_t *)slo + so, sb, cudaMemcpyHostToDevice, hp->in);
-        if (e == cudaSuccess) e = cudaEventRecord(hp->ev_in[k & 63], hp->in);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, hp->ev_in[k & 63], 0);
+        if (e == cudaSuccess) e = cudaEventRecord(hp->ev_in[k], hp->in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, hp->ev_in[k], 0);
         if (e != cudaSuccess) break;
         GmatbImage sc = sdev, dc = ddev;
         sc.batch = fn; dc.batch = fn;
@@ -653,8 +679,8 @@ extern "C" int gmatb_sws_scale_host(GmatbSws *c, const GmatbImage *src_host, con
         }
         rc = scale_batch(c, &sc, &dc);
         if (rc) break;
-        e = cudaEventRecord(hp->ev_k[k & 63], c->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->out, hp->ev_k[k & 63], 0);
+        e = cudaEventRecord(hp->ev_k[k], c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->out, hp->ev_k[k], 0);
         if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t *)dlo + dofs, dd + dofs, db, cudaMemcpyDeviceToHost, hp->out);
     }
     cudaError_t e2 = cudaStreamSynchronize(hp->in);

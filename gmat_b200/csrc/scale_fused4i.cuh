@@ -33,7 +33,7 @@
 
 namespace gmatb {
 
-#define GMATB_F4I_DENSE 24   /* more ambiguous outputs than this in one warp step: the band continues in float */
+#define GMATB_F4I_DENSE 8    /* more ambiguous outputs than this in one warp step: the band continues in float */
 #define GMATB_F4I_RING  (4 * 32 * 12)   /* words: the packed rows of the last 4 steps of every lane */
 
 // d = c + sum_i a.u8[i] * b.s8[i]
@@ -47,17 +47,15 @@ __host__ __device__ constexpr uint32_t s8x4(int b0, int b1, int b2, int b3) {
 // One ambiguous output -- channel c of output column xo (0..3) of lane `src_lane`, output row k-1, found while
 // pair k is processed -- recomputed with the float chain (the operations of scale_fused3.cuh /
 // resample_core.cuh) from the quantised bytes the last steps left in the shared-memory ring.  The whole warp
-// takes part: lane r (0..3) does the horizontal chain of source row 2(k-1)-1+r, then everybody the vertical one.
-// Returns the output value.
+// takes part: lane r (0..3) does the horizontal chain of source row 2(k-1)-1+r (`row` = that row's words in the
+// ring: b[k-2], t[k-1], b[k-1], t[k]), then everybody the vertical one.  Returns the output value.
 template <bool WRAP>
-__device__ __forceinline__ int fused4i_fix(const Fused3Params &P, const uint32_t *ring, int k, int src_lane, int xo, int c, int lane) {
-    const int r = lane & 3;
-    const int kk = k - 2 + ((r + 1) >> 1);                      // rows: b[k-2], t[k-1], b[k-1], t[k]
-    const uint32_t *row = ring + (kk & 3) * (32 * 12) + ((r & 1) ? 0 : 6) + 2 * c;
+__device__ __forceinline__ int fused4i_fix(const Fused3Params &P, const uint32_t *row, int src_lane, int xo, int c) {
     // the window of 4 bytes starts at byte 3 + 2 xo of (left lane's columns 4..7 | own 0..3 | own 4..7 | right lane's 0..3)
-    const uint32_t *plo = row + (xo == 0 ? (src_lane - 1) * 12 + 1 : xo == 3 ? src_lane * 12 + 1 : src_lane * 12);
-    const uint32_t *phi = row + (xo == 0 ? src_lane * 12 : xo == 3 ? (src_lane + 1) * 12 : src_lane * 12 + 1);
-    const uint32_t w = __funnelshift_r(*plo, *phi, (xo & 1) ? 8 : 24);
+    const int a = src_lane * 12 + 2 * c;
+    const int olo = xo == 0 ? a - 11 : xo == 3 ? a + 1 : a;
+    const int ohi = xo == 0 ? a : xo == 3 ? a + 12 : a + 1;
+    const uint32_t w = __funnelshift_r(row[olo], row[ohi], (xo & 1) ? 8 : 24);
     const float p0 = norm_inrange(byte_magic<0>(w), P.nk), p1 = norm_inrange(byte_magic<1>(w), P.nk);
     const float p2 = norm_inrange(byte_magic<2>(w), P.nk), p3 = norm_inrange(byte_magic<3>(w), P.nk);
     float h = __fmul_rn(P.wx[1], p1);
@@ -205,14 +203,26 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
     const unsigned pitch_d = P.dst.pl[0].pitch;
     const bool lrep = strip < 0, rrep = strip >= nstrips;
 
-    // row pair kk, rows clamped to the frame (pairs -1 and HC replicate the first / last row); kk is warp-uniform
-    auto load_pair = [&](int kk, Row &R) {
-        const unsigned rt = (unsigned)min(max(2 * kk, 0), H - 1), rb = (unsigned)min(max(2 * kk + 1, 0), H - 1);
+    // Warp-uniform byte offsets of the rows of the pair that is loaded next.  Rows are clamped to the frame (pairs
+    // -1 and HC replicate the first / last row): inside the loop the offsets advance by whole pairs, except into
+    // pair HC.
+    unsigned ot, ob, oc, oc2;
+    auto seek = [&](int kk) {
+        ot = (unsigned)min(max(2 * kk, 0), H - 1) * pitch_y; ob = (unsigned)min(max(2 * kk + 1, 0), H - 1) * pitch_y;
         const unsigned rc = (unsigned)min(max(kk, 0), HC - 1);
-        R.yt = ldg64(py + rt * pitch_y); R.yb = ldg64(py + rb * pitch_y);
-        if (L == L_NV12) R.c0 = ldg64(pu + rc * pitch_c);
-        else { R.c0.x = ldg32(pu + rc * pitch_c); R.c0.y = ldg32(pv + rc * pitch_c2); }
+        oc = rc * pitch_c; oc2 = rc * pitch_c2;
+    };
+    auto load_here = [&](Row &R) {
+        R.yt = ldg64(py + ot); R.yb = ldg64(py + ob);
+        if (L == L_NV12) R.c0 = ldg64(pu + oc);
+        else { R.c0.x = ldg32(pu + oc); R.c0.y = ldg32(pv + oc2); }
         if (edge) edge_replicate<L, 8>(R, lrep, rrep);
+    };
+    const unsigned sy = 2 * pitch_y;
+    auto load_next = [&](Row &R, int kk) {      // loads pair kk >= 1 (the offsets are on it), then moves them to pair kk+1
+        load_here(R);
+        if (kk + 1 < HC) { ot += sy; ob += sy; oc += pitch_c; oc2 += pitch_c2; }
+        else ot = ob;                           // pair HC: rows H-1, H-1, chroma row HC-1
     };
 
     int Pacc[4][3], Ta[4][3], N[4][3];
@@ -247,7 +257,10 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
         if (total > GMATB_F4I_DENSE) return true;
         __syncwarp();                       // this step's ring stores and output stores are visible to the whole warp
         uint32_t act = __ballot_sync(0xffffffffu, mask != 0u);
-        uint8_t *row = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + (long long)(k - 1) * (long long)pitch_d;
+        uint8_t *orow = P.dst.pl[0].p + fz * P.dst.pl[0].bstride + (long long)(k - 1) * (long long)pitch_d
+                      + ((long long)blockIdx.x * OWN - 1) * (4 * dst_bpp(DST));
+        const int r = lane & 3;
+        const uint32_t *rrow = ring + ((k - 2 + ((r + 1) >> 1)) & 3) * (32 * 12) + ((r & 1) ? 0 : 6);
         while (act) {
             const int l = __ffs(act) - 1;
             act &= act - 1;
@@ -256,9 +269,8 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
                 const int i = __ffs(mk) - 1;
                 mk &= mk - 1;
                 const int xo = i / 3, c = i - 3 * xo;
-                const int o = fused4i_fix<WRAP>(P, ring, k, l, xo, c, lane);
-                if (lane == 0)
-                    row[(size_t)((blockIdx.x * OWN + l - 1) * 4 + xo) * dst_bpp(DST) + (dst_swap(DST) ? 2 - c : c)] = (uint8_t)o;
+                const int o = fused4i_fix<WRAP>(P, rrow, l, xo, c);
+                if (lane == 0) orow[(l * 4 + xo) * dst_bpp(DST) + (dst_swap(DST) ? 2 - c : c)] = (uint8_t)o;
             }
         }
         return false;
@@ -266,8 +278,9 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
 
     Row A, B;
     int k = kfirst;
-    load_pair(k, A);
-    load_pair(k + 1, B);
+    seek(k); load_here(A);
+    seek(k + 1); load_here(B);
+    seek(k + 2);
     bool dense = false;
     uint32_t *lane_ring = ring + lane * 12;
 #pragma unroll 1
@@ -275,7 +288,7 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
         {
             const bool st = owner && k >= kstore;
             const uint32_t um = F::step(P, A, Pacc, Ta, N, st, pd, alpha_i, lane_ring + (k & 3) * (32 * 12),
-                                        [&](Row &R) { if (k + 2 <= klast) load_pair(k + 2, R); });
+                                        [&](Row &R) { if (k + 2 <= klast) load_next(R, k + 2); });
             if (__any_sync(0xffffffffu, st && um < 12u) && ambiguous(st, k)) { dense = true; break; }
             pd += pitch_d;
             if (++k > klast) break;
@@ -283,7 +296,7 @@ __device__ __forceinline__ void fused4i_band(const Fused3Params &P, uint32_t *ri
         {
             const bool st = owner && k >= kstore;
             const uint32_t um = F::step(P, B, Pacc, Ta, N, st, pd, alpha_i, lane_ring + (k & 3) * (32 * 12),
-                                        [&](Row &R) { if (k + 2 <= klast) load_pair(k + 2, R); });
+                                        [&](Row &R) { if (k + 2 <= klast) load_next(R, k + 2); });
             if (__any_sync(0xffffffffu, st && um < 12u) && ambiguous(st, k)) { dense = true; break; }
             pd += pitch_d;
             if (++k > klast) break;

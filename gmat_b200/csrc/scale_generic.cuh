@@ -170,9 +170,11 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
 #pragma unroll
                 for (int k = 0; k < SB; k++) { R.c[k] = __ldg(reinterpret_cast<const uint32_t *>(qc) + k); R.c2[k] = 0; }
             } else {
+                // the U and V planes have their own strides (linesize[1] / linesize[2])
                 const size_t co = (size_t)(Y >> 1) * P.src.pl[1].pitch + (size_t)(X >> 1) * SB;
-                if (SBITS == 8) { R.c[0] = __ldg(reinterpret_cast<const uint16_t *>(bu + co)); R.c2[0] = __ldg(reinterpret_cast<const uint16_t *>(bv + co)); }
-                else { R.c[0] = __ldg(reinterpret_cast<const uint32_t *>(bu + co)); R.c2[0] = __ldg(reinterpret_cast<const uint32_t *>(bv + co)); R.c[SB - 1] = R.c[0]; R.c2[SB - 1] = R.c2[0]; }
+                const size_t cv = (size_t)(Y >> 1) * P.src.pl[2].pitch + (size_t)(X >> 1) * SB;
+                if (SBITS == 8) { R.c[0] = __ldg(reinterpret_cast<const uint16_t *>(bu + co)); R.c2[0] = __ldg(reinterpret_cast<const uint16_t *>(bv + cv)); }
+                else { R.c[0] = __ldg(reinterpret_cast<const uint32_t *>(bu + co)); R.c2[0] = __ldg(reinterpret_cast<const uint32_t *>(bv + cv)); R.c[SB - 1] = R.c[0]; R.c2[SB - 1] = R.c2[0]; }
             }
         };
         auto convert = [&](const Raw &R, int lx, int ly) {
@@ -248,8 +250,9 @@ __global__ void __launch_bounds__(256) generic_scale_kernel(const GenParams P) {
                         else { u = reinterpret_cast<const uint16_t *>(q)[0]; v = reinterpret_cast<const uint16_t *>(q)[1]; }
                     } else {
                         const size_t co = (size_t)ccy * P.src.pl[1].pitch + (size_t)ccx * SB;
-                        if (SBITS == 8) { u = bu[co]; v = bv[co]; }
-                        else { u = *reinterpret_cast<const uint16_t *>(bu + co); v = *reinterpret_cast<const uint16_t *>(bv + co); }
+                        const size_t cv = (size_t)ccy * P.src.pl[2].pitch + (size_t)ccx * SB;
+                        if (SBITS == 8) { u = bu[co]; v = bv[cv]; }
+                        else { u = *reinterpret_cast<const uint16_t *>(bu + co); v = *reinterpret_cast<const uint16_t *>(bv + cv); }
                     }
                     const float fy = __uint_as_float(0x4B000000u | y) - (GMATB_MAGIC + low);
                     const float fu = __uint_as_float(0x4B000000u | u) - (GMATB_MAGIC + mid);

@@ -2,11 +2,14 @@
 // its own translation unit so that it builds in parallel with scale.cu.
 #include "scale_fused4i.cuh"
 
+#ifndef GMATB_INT_MINB
+#define GMATB_INT_MINB 16
+#endif
 namespace gmatb {
 
 template <int L, int DST>
 static void launch_int_t(int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
-#define K(W, A, B, S) fused_csc_scale2_int_kernel<L, DST, W, A, B, S, 16><<<g, 32, 0, st>>>(P)
+#define K(W, A, B, S) fused_csc_scale2_int_kernel<L, DST, W, A, B, S, GMATB_INT_MINB><<<g, 32, 0, st>>>(P)
     if (wrap) { if (iw == 1) K(true, -3, 19, 5); else if (iw == 2) K(true, -1, 9, 4); else K(true, -1, 5, 3); }
     else      { if (iw == 1) K(false, -3, 19, 5); else if (iw == 2) K(false, -1, 9, 4); else K(false, -1, 5, 3); }
 #undef K

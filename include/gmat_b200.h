@@ -90,9 +90,10 @@ extern "C" {
  * scale_cuda kernels' missing upper clamp (values >= 256 wrap modulo 256,
  * vf_scale_cuda.cu:1057-1071 + cvt.rzi) instead of saturating. */
 #define GMATB_SWS_PARITY_WRAP   0x40000000
-/* gmat_b200 extension bit: keep the fused 2:1 kernel on the float chain where the exact-integer form
- * (dyadic bicubic weights, scale_fused4i.cuh) would apply.  Same output bytes; for A/B tests and timing. */
-#define GMATB_SWS_FLOAT_CHAIN   0x20000000
+/* gmat_b200 extension bit: run the exact-integer form of the fused 2:1 kernel (scale_fused4i.cuh) where it
+ * applies (8-bit yuv sources, dyadic bicubic weights: param0 = 0.75, 0.5, 1.0).  Same output bytes as the default
+ * float-chain kernel (tests/test_gpu_scale_int.py); measured slower on B200, hence opt-in. */
+#define GMATB_SWS_INT_CHAIN     0x20000000
 
 /* ---- interpolation / border codes of the filter layer (NVCV numbering:
  *      NVCV_INTERP_* / NVCV_BORDER_* as used by vf_rotate_nvcv.c:115-135 and
@@ -101,6 +102,9 @@ extern "C" {
 #define GMATB_INTERP_LINEAR  1
 #define GMATB_INTERP_CUBIC   2
 #define GMATB_INTERP_AREA    3
+
+#define GMATB_MEDIAN_MAXK 15   /* gmatb_median: odd kw, kh <= this */
+#define GMATB_GAUSS_MAXK  31   /* gmatb_gaussian: odd kw, kh <= this */
 
 #define GMATB_BORDER_CONSTANT   0
 #define GMATB_BORDER_REPLICATE  1
@@ -129,6 +133,9 @@ int         gmatb_last_cuda_error(void);        /* cudaError_t of the last failu
 const char *gmatb_last_cuda_error_string(void);
 long long   gmatb_launch_count(void);           /* kernels launched by this library so far */
 int         gmatb_device_sync(void);
+/* Sink for the library's diagnostics (e.g. an interpolation mode that falls back to another one); NULL = stderr.
+ * The FFmpeg-side glue passes a function that forwards to av_log. */
+void        gmatb_set_log(void (*cb)(const char *msg));
 
 /* 3x3 matrices exactly as the reference computes them (yuv2rgb_cuda.cu:782-848):
  * float arithmetic for the entries, double for the range scale, cast to float. */

@@ -1,4 +1,4 @@
-"""-m gpu: the exact-integer form of the fused 2:1 kernel (scale_fused4i.cuh) against the float-chain
+"""-m gpu: the exact-integer form of the fused 2:1 kernel (scale_fused4i.cuh, opt-in: SWS.INT_CHAIN) against the float-chain
 kernel (scale_fused3.cuh, itself pinned to the reference's kernels in test_gpu_scale.py) and the CPU
 oracle, on content that exercises each of its three regimes: no ambiguous outputs, a few per warp
 step (shared-memory queue + per-output float recomputation), many (the band continues in float)."""
@@ -61,8 +61,8 @@ def run_pair(dev, sfmt, dfmt, sw, sh, n, kind, param, wrap, seed=1):
     src.upload(host)
     ds = src.to(dev)
     fl = SWS.BICUBIC | HW | (SWS.PARITY_WRAP if wrap else 0)
-    ci = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl, param)
-    cf = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.FLOAT_CHAIN, param)
+    ci = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.INT_CHAIN, param)
+    cf = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl, param)
     assert ci.path == 1 and cf.path == 1
     a = FrameBatch(dfmt, dw, dh, n, device=dev); b = FrameBatch(dfmt, dw, dh, n, device=dev)
     a.buf.fill_(0xA5); b.buf.fill_(0xA5)
@@ -99,7 +99,7 @@ def test_int_headline_4k(dev, kind):
 
 
 def test_int_selected_only_for_dyadic_weights(dev):
-    """other parameters keep the float chain (same bytes either way: FLOAT_CHAIN is then a no-op)"""
+    """other parameters keep the float chain (INT_CHAIN is then a no-op)"""
     for param in ((0.6,), (0.3,), None):
         _, _, a, b = run_pair(dev, FMT.NV12, FMT.RGB24, 512, 130, 1, "noise", param, False)
         assert torch.equal(a.buf, b.buf)

@@ -273,3 +273,52 @@ def test_median3_column_sort_identity():
     assert np.array_equal(got, np.median(w.reshape(-1, 9), axis=1).astype(np.int64))
     b = np.arange(256)
     assert np.all(np.diff(b * 257) > 0) and np.all((b * 257) & 0xFF == b) and (255 * 257) < 65536
+
+
+# ---- the exactness argument behind the integer form of the fused 2:1 kernel (scale_fused4i.cuh) -------------
+def _fma32(a, b, c):
+    """float32 fma on arrays: the product of two float32 is exact in float64; the float64 sum is then rounded to
+    float32 (double rounding can differ from a true fma only on exact float32 ties of the float64 sum, ~2^-29 of
+    the cases, and by one float32 ulp -- far inside the margin asserted below)"""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def _chain4(w, p0, p1, p2, p3):
+    t = (w[1] * p1).astype(np.float32)
+    t = _fma32(np.float32(w[0]), p0, t); t = _fma32(np.float32(w[2]), p2, t); t = _fma32(np.float32(w[3]), p3, t)
+    return t
+
+
+@pytest.mark.parametrize("a,b,s", [(-3, 19, 5), (-1, 9, 4), (-1, 5, 3)])
+def test_integer_form_of_the_dyadic_2to1_chain(a, b, s):
+    """R-B bicubic at exactly 2:1 with param0 = 0.75 / 0.5 / 1.0 has weights (a, b, b, a) / 2^s.  On the quantised
+    bytes j the exact value of 255 v is N / 2^(2s) with N = sum W[y] W[x] j[y][x]; the float chain the reference
+    runs (vf_scale_cuda.cu:1040-1074: p = RN(j/255), two 4-tap FMA chains, trunc(255 v)) stays within 2.5e-4 of it,
+    so it truncates to N >> 2s whenever N is not a multiple of 2^(2s) -- what the integer kernel stores -- and
+    can land on either side only when it is (those outputs are recomputed with the float chain)."""
+    rng = np.random.default_rng(1234 + s)
+    n = 400_000
+    w = np.array([a, b, b, a], np.float32) / np.float32(1 << s)
+    wi = np.array([a, b, b, a], np.int64)
+    mode = rng.integers(0, 4, n)
+    base = rng.integers(0, 256, n)
+    amp = np.array([256, 16, 2, 1])[mode]
+    j = (base[:, None, None] * (mode != 0)[:, None, None] + rng.integers(0, 1 << 30, (n, 4, 4)) % amp[:, None, None])
+    sat = rng.integers(0, 8, (n, 4, 4))
+    j = np.where((mode == 0)[:, None, None] & (sat == 0), 0, np.where((mode == 0)[:, None, None] & (sat == 1), 255, j))
+    j = np.clip(j, 0, 255)
+    p = (j.astype(np.float64) / 255.0).astype(np.float32)          # RN(j/255)
+    h = [_chain4(w, p[:, y, 0], p[:, y, 1], p[:, y, 2], p[:, y, 3]) for y in range(4)]
+    v = _chain4(w, h[0], h[1], h[2], h[3])
+    f = (v * np.float32(255.0)).astype(np.float32)
+    got = np.where(f < 0, 0, np.trunc(f)).astype(np.int64)
+    N = np.einsum("y,x,nyx->n", wi, wi, j.astype(np.int64))
+    sh = 2 * s
+    E = np.where(N < 0, 0, N >> sh)
+    err = np.abs(f.astype(np.float64) - N / float(1 << sh)).max()
+    assert err < 2.5e-4 < 1.0 / (1 << sh) / 2 or sh > 10, err
+    unamb = (N & ((1 << sh) - 1)) != 0
+    assert np.array_equal(got[unamb], E[unamb])
+    amb = ~unamb & (N > 0)
+    assert amb.sum() > 1000 and np.all((got[amb] == E[amb]) | (got[amb] == E[amb] - 1))
+    assert (got[amb] != E[amb]).any(), "the ambiguous outputs do need the float chain"
