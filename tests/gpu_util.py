@@ -123,3 +123,46 @@ def o2_packed(func, src, dst, ch, depth, param=999999.0, linear=0, integer=0, pl
                          (vp * 4)(*pad([di.data[plane]])), dw, dh, di.linesize[plane], sw, sh, C.c_float(param), linear, integer)
     assert rc == 0, (func, rc)
     torch.cuda.synchronize()
+
+
+_o2c = None
+
+
+def o2_coeffs(lanczos, fx, param=999999.0):
+    """the reference's own lanczos_coeffs / bicubic_coeffs (vf_scale_cuda.cu:948-981) at the positions fx"""
+    global _o2c
+    if _o2c is None:
+        _o2c = C.CDLL(os.path.join(REF, "libref_o2_coeffs.so"))
+        _o2c.ref_o2_coeffs.argtypes = [ci, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), ci]
+    fx = np.ascontiguousarray(fx, np.float32)
+    out = np.zeros((len(fx), 4), np.float32)
+    rc = _o2c.ref_o2_coeffs(int(lanczos), fx.ctypes.data_as(C.POINTER(C.c_float)), param,
+                            out.ctypes.data_as(C.POINTER(C.c_float)), len(fx))
+    assert rc == 0, rc
+    return out
+
+
+_O2_FMT = {FMT.NV12: ("nv12", 8, (1, 2)), FMT.YUV420P: ("yuv420p", 8, (1, 1, 1)),
+           FMT.P010LE: ("p010le", 16, (1, 2)), FMT.P016LE: ("p016le", 16, (1, 2))}
+
+
+def o2_frame(algo, src, dst, param=999999.0):
+    """one frame through the reference's scale_cuda kernels exactly as scalecuda_resize does it
+    (vf_scale_cuda.c:430-500): a texture per input plane, the luma launch, then the _uv launch on the chroma grid"""
+    L = o2()
+    name, depth, chans = _O2_FMT[src.fmt]
+    assert dst.fmt == src.fmt
+    si, di = src.image(), dst.image()
+    npl = len(chans)
+    cw, chh = (src.w + 1) // 2, (src.h + 1) // 2
+    dcw, dch = (dst.w + 1) // 2, (dst.h + 1) // 2
+    pad = lambda xs: list(xs) + [0] * (4 - len(xs))
+    args = ((vp * 4)(*pad([si.data[i] for i in range(npl)])), (ci * 4)(*pad([si.linesize[i] for i in range(npl)])),
+            (ci * 4)(*pad([src.w] + [cw] * (npl - 1))), (ci * 4)(*pad([src.h] + [chh] * (npl - 1))),
+            (ci * 4)(*pad([depth] * npl)), (ci * 4)(*pad(chans)), (vp * 4)(*pad([di.data[i] for i in range(npl)])))
+    fn = f"Subsample_{algo}_{name}_{name}"
+    rc = L.ref_o2_launch(fn.encode(), npl, *args, dst.w, dst.h, di.linesize[0], src.w, src.h, C.c_float(param), 0, 0)
+    assert rc == 0, (fn, rc)
+    rc = L.ref_o2_launch((fn + "_uv").encode(), npl, *args, dcw, dch, di.linesize[1], cw, chh, C.c_float(param), 0, 0)
+    assert rc == 0, (fn + "_uv", rc)
+    torch.cuda.synchronize()

@@ -207,18 +207,28 @@ def test_packed_resample_vs_reference_scale_cuda_live(dev, algo, flag, param, op
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("algo,flag,oparam", [("Bicubic", SWS.BICUBIC, 999999.0), ("Lanczos", SWS.LANCZOS, 999999.0)])
-def test_fused_pipeline_vs_reference_two_kernel_pipeline_live(dev, algo, flag, oparam):
+@pytest.mark.parametrize("algo,flag,param,oparam", [("Bicubic", SWS.BICUBIC, None, 999999.0), ("Bicubic", SWS.BICUBIC, (0.75,), 0.75),
+                                                    ("Bicubic", SWS.BICUBIC, (0.5,), 0.5), ("Lanczos", SWS.LANCZOS, None, 999999.0)])
+@pytest.mark.parametrize("sw,sh", [(1920, 1080), (3840, 2160)])
+@pytest.mark.parametrize("extra", [0, SWS.INT_CHAIN])
+def test_fused_pipeline_vs_reference_two_kernel_pipeline_live(dev, algo, flag, param, oparam, sw, sh, extra):
     """The reference's unfused pipeline rebuilt from its own kernels: O1 nv12->rgba at source size, then
-    O2 Subsample_*_rgb0_rgb0.  Our fused kernel (rgba output) must reproduce its r,g,b bytes exactly."""
-    sw, sh, dw, dh = 1920, 1080, 960, 540
+    O2 Subsample_*_rgb0_rgb0.  Our fused kernel (rgba output) must reproduce its r,g,b bytes exactly -- including
+    the BASELINE C2 headline itself (param0 = 0.75 at 3840x2160 -> 1920x1080), on both forms of the kernel."""
+    dw, dh = sw // 2, sh // 2
     src = FrameBatch(FMT.NV12, sw, sh, 1, device=dev); src.fill_lcg(seed=99)
     mid = FrameBatch(FMT.RGBA, sw, sh, 1, device=dev); o1_run("yuv2rgb_cuda", src, mid, 0)
     ref = FrameBatch(FMT.RGBA, dw, dh, 1, device=dev); o2_packed(f"Subsample_{algo}_rgb0_rgb0", mid, ref, 4, 8, oparam)
-    c = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.RGBA, flag | HW | SWS.PARITY_WRAP)
+    c = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.RGBA, flag | HW | SWS.PARITY_WRAP | extra, param)
     assert c.path == 1
     dd = FrameBatch(FMT.RGBA, dw, dh, 1, device=dev); c.scale(src, dd); torch.cuda.synchronize()
-    assert_same(dd, ref, f"fused vs O1+O2 {algo}")
+    assert_same(dd, ref, f"fused vs O1+O2 {algo} {param} {sw}x{sh}")
+    # the headline output format: same bytes without the alpha channel, production clamp where the reference wrapped
+    c3 = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.RGB24, flag | HW | extra, param)
+    d3 = FrameBatch(FMT.RGB24, dw, dh, 1, device=dev); c3.scale(src, d3); torch.cuda.synchronize()
+    a = d3.plane_view(d3.numpy(), 0, 0).reshape(dh, dw, 3)
+    b = ref.plane_view(ref.numpy(), 0, 0).reshape(dh, dw, 4)[:, :, :3]
+    assert np.all((a == b) | (a == 255)) and (a != b).mean() < 0.2
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
@@ -241,6 +251,45 @@ def test_plane_scaling_vs_reference_nv12_kernels_live(dev):
     c = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.NV12, SWS.BICUBIC | HW | SWS.PARITY_WRAP, (0.75,))
     dd = FrameBatch(FMT.NV12, dw, dh, 1, device=dev); c.scale(src, dd); torch.cuda.synchronize()
     assert_same(dd, ref, "nv12->nv12 bicubic vs O2")
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("fmt", [FMT.NV12, FMT.YUV420P, FMT.P010LE, FMT.P016LE])
+@pytest.mark.parametrize("algo,flag,param,oparam", [("Bicubic", SWS.BICUBIC, None, 999999.0), ("Bicubic", SWS.BICUBIC, (0.75,), 0.75),
+                                                    ("Lanczos", SWS.LANCZOS, None, 999999.0)])
+@pytest.mark.parametrize("sw,sh,dw,dh", [(640, 360, 400, 226), (256, 144, 128, 72), (136, 68, 200, 100), (1920, 1080, 1280, 720)])   # planes 512-byte aligned: textures
+def test_yuv_plane_scaling_vs_reference_scale_cuda_live(dev, fmt, algo, flag, param, oparam, sw, sh, dw, dh):
+    """yuv -> same yuv format at another size = what the scale_cuda filter does: every plane of NV12 / YUV420P / P010 /
+    P016 against Subsample_{Bicubic,Lanczos}_<fmt>_<fmt>[_uv] of the reference, launched like scalecuda_resize
+    (vf_scale_cuda.c:430-500); 16-bit planes included (they were only checked on constant frames before)."""
+    from gpu_util import o2_frame
+    src = FrameBatch(fmt, sw, sh, 1, device=dev); src.fill_lcg(seed=sw + dh)
+    ref = FrameBatch(fmt, dw, dh, 1, device=dev); ref.buf.fill_(0)
+    o2_frame(algo, src, ref, oparam)
+    c = SwsContext(sw, sh, fmt, dw, dh, fmt, flag | HW | SWS.PARITY_WRAP, param)
+    dd = FrameBatch(fmt, dw, dh, 1, device=dev); dd.buf.fill_(0)
+    c.scale(src, dd); torch.cuda.synchronize()
+    assert_same(dd, ref, f"{fmt} {algo}{param} {sw}x{sh}->{dw}x{dh} vs O2")
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_device_filter_tables_vs_reference_coeff_functions_live(dev):
+    """our filter_table_kernel against the reference's own lanczos_coeffs / bicubic_coeffs (vf_scale_cuda.cu:948-981,
+    #included in place by oracle/ref_o2_coeffs.cu) at the same fractional positions: bit-exact, Lanczos' fast-math
+    sines included"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_lanczos import frac_positions
+    from gpu_util import o2_coeffs
+    for (s_, d_) in ((3840, 1920), (7680, 3840), (1920, 1281), (33, 50), (100, 12), (1080, 720), (64, 40)):
+        fx, pos = frac_positions(s_, d_)
+        for flag, param, lz, op in ((SWS.LANCZOS, None, 1, 999999.0), (SWS.BICUBIC, None, 0, 999999.0), (SWS.BICUBIC, (0.75,), 0, 0.75),
+                                    (SWS.BICUBIC, (0.6,), 0, 0.6)):
+            c = SwsContext(s_, 64, FMT.NV12, d_, 32, FMT.RGB24, flag | HW, param)
+            co, po = c.get_filter(0)
+            ref = o2_coeffs(lz, fx, op)
+            assert np.array_equal(po, pos), (s_, d_)
+            assert np.array_equal(co.view(np.uint32), ref.view(np.uint32)), (s_, d_, flag, param, int((co != ref).sum()))
 
 
 @pytest.mark.parametrize("fmt", [FMT.YUV420P, FMT.NV12, FMT.P010LE, FMT.P016LE, FMT.RGB0, FMT.BGR0])

@@ -1,6 +1,7 @@
 """CPU tests of the oracle (oracle/gmat_oracle.c): known-answer tests from SURVEY 8a and the
 golden vectors produced by the REFERENCE's own CUDA kernels on a B200
 (tests/golden/make_golden.py -> tests/golden/reference_gpu_golden.npz)."""
+import os
 import re
 
 import numpy as np
@@ -181,18 +182,24 @@ def _o2_cases(golden):
 
 def test_oracle_vs_reference_resample_golden(golden):
     """O2 golden vectors (the reference's scale_cuda kernels) vs the CPU restatement of R-B.
-    Bicubic / nearest coefficient tables are computed on the CPU (bit-exact restatement);
-    Lanczos tables need the GPU's __sinf and are covered by the -m gpu tests."""
+    Bicubic / nearest coefficient tables are computed on the CPU (bit-exact restatement); Lanczos tables need the
+    GPU's fast-math __sinf, so the committed tables of the reference's own lanczos_coeffs
+    (tests/golden/reference_lanczos_tables.npz, made by make_golden_lanczos.py on a B200) are used: the resample
+    arithmetic of the oracle is pinned for Lanczos -- C3's filter -- as well."""
     import ctypes as C
     L = orc.orc()
-    n = 0
+    lz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_lanczos_tables.npz"))
+    n = nl = 0
     for name, algo, pn, kind, (sw, sh, dw, dh) in _o2_cases(golden):
-        if algo == "Lanczos":
-            continue
         A = 0.0 if pn == "def" else -float(pn)
-        a = orc.ALGO["bicubic"] if algo == "Bicubic" else orc.ALGO["nearest"]
-        cx, px = orc.filter_table(a, sw, dw, A)
-        cy, py = orc.filter_table(a, sh, dh, A)
+        if algo == "Lanczos":
+            cx, px = np.ascontiguousarray(lz[f"lanczos_{sw}_{dw}"]), np.ascontiguousarray(lz[f"pos_{sw}_{dw}"])
+            cy, py = np.ascontiguousarray(lz[f"lanczos_{sh}_{dh}"]), np.ascontiguousarray(lz[f"pos_{sh}_{dh}"])
+            nl += 1
+        else:
+            a = orc.ALGO["bicubic"] if algo == "Bicubic" else orc.ALGO["nearest"]
+            cx, px = orc.filter_table(a, sw, dw, A)
+            cy, py = orc.filter_table(a, sh, dh, A)
         ra = 1 if algo == "Nearest" else 0
         if kind == "rgb0":
             src = FrameBatch(FMT.RGBA, sw, sh, 1); src.fill_lcg(seed=31 + sw + dw)
@@ -214,7 +221,26 @@ def test_oracle_vs_reference_resample_golden(golden):
         bad = int((got != exp).sum())
         assert bad == 0, f"{name}: {bad} of {got.size} bytes differ from the reference scale_cuda output"
         n += 1
-    assert n >= 40
+    assert n >= 40 and nl >= 12
+
+
+def test_reference_tables_vs_cpu_restatement():
+    """the committed reference tables: positions and the bicubic rows are reproduced bit for bit on the CPU (which
+    validates how the fractional positions fed to the reference's functions were formed); the CPU's libm Lanczos
+    stays within 2e-6 of the reference's fast-math one"""
+    lz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_lanczos_tables.npz"))
+    n = 0
+    for k in lz.files:
+        if not k.startswith("lanczos_"):
+            continue
+        sn, dn = (int(v) for v in k.split("_")[1:])
+        co, po = orc.filter_table(orc.ALGO["bicubic"], sn, dn, -0.75)
+        assert np.array_equal(po, lz[f"pos_{sn}_{dn}"])
+        assert np.array_equal(co.view(np.uint32), lz[f"bicubic075_{sn}_{dn}"].view(np.uint32)), k
+        cl, _ = orc.filter_table(orc.ALGO["lanczos"], sn, dn)
+        assert np.abs(cl - lz[k]).max() < 2e-6, k
+        n += 1
+    assert n >= 20
 
 
 # ---- exactness arguments the kernels lean on, checked in IEEE binary32 on the CPU -------------------------------
