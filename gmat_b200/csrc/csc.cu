@@ -187,7 +187,9 @@ __device__ __forceinline__ void store_rgb_px(uint8_t *p, int r, int g, int b) {
 // ---------------------------------------------------------------------------
 // yuv -> packed rgb
 // ---------------------------------------------------------------------------
-template <int L, int SBITS, int DST, bool SPARSE>
+// FMAF: which of the reference's two roundings of the chain (csc_core.cuh): libgpuscale's 8-bit kernels compile to
+// the FADD form, its 16-bit kernels and every kernel of metrans' NvCodec/ColorSpace.cu to the FMA form.
+template <int L, int SBITS, int DST, bool SPARSE, bool FMAF = (SBITS == 16)>
 #ifndef GMATB_Y2R_MINB
 #define GMATB_Y2R_MINB 4
 #endif
@@ -208,12 +210,12 @@ __global__ void __launch_bounds__(256, GMATB_Y2R_MINB) yuv2rgb_kernel(Img src, I
     for (int j = 0; j < 4; j++) {
         float fu, fv;
         upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-        ChromaTerms t = chroma_terms<SPARSE, SBITS == 16>(fu, fv, M);
+        ChromaTerms t = chroma_terms<SPARSE, FMAF>(fu, fv, M);
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
-            csc_pair_i<SPARSE, SBITS == 16>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
-                                            b[rr][2 * j], b[rr][2 * j + 1]);
+            csc_pair_i<SPARSE, FMAF>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
+                                     b[rr][2 * j], b[rr][2 * j + 1]);
         }
     }
     constexpr int BPP = dst_bpp(DST);
@@ -295,6 +297,70 @@ __global__ void __launch_bounds__(256) yuv2rgb_planar_f32_kernel(Img src, Img ds
     }
 }
 
+
+// NV12 / P016 -> three stacked planes of 8-bit or float components, FMA form: metrans NvCodec/ColorSpace.cu
+// YuvToRgbPlanarKernel (:163-190) -- the chain, clamp to the source range, 16-bit results >> 8, then the byte itself
+// or v / 255 (IEEE division: a 256-entry table of the exact quotients per block).  SWAP: plane order B, G, R.
+template <int SBITS, bool OUTF, bool SWAP, bool SPARSE>
+__global__ void __launch_bounds__(256) yuv2rgb_planar8_kernel(Img src, uint8_t *dst, int dpitch, long long plane_stride, Mat9 M, int vec_ok) {
+    __shared__ float tab[256];
+    if (OUTF) {
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        tab[t] = __fdiv_rn((float)t, 255.0f);
+        __syncthreads();
+    }
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
+    if (x0 >= src.w || y0 >= src.h) return;
+    const bool full = vec_ok && (x0 + 8 <= src.w) && (y0 + 2 <= src.h);
+    float ym[2][8], um[4], vm[4];
+    load_yuv_tile<L_NV12, SBITS>(src, 0, x0, y0, full, ym, um, vm);
+    constexpr float YB = -(GMATB_MAGIC + (SBITS == 8 ? 16.f : 4096.f));
+    constexpr float CB = -(GMATB_MAGIC + (SBITS == 8 ? 128.f : 32768.f));
+    constexpr int SMAX = SBITS == 8 ? 255 : 65535;
+    int c[3][2][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float fu, fv;
+        upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+        ChromaTerms t = chroma_terms<SPARSE, true>(fu, fv, M);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
+            csc_pair_i<SPARSE, true>(fy2, t, M, c[0][rr][2 * j], c[0][rr][2 * j + 1], c[1][rr][2 * j], c[1][rr][2 * j + 1],
+                                     c[2][rr][2 * j], c[2][rr][2 * j + 1]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        const int ch = SWAP ? 2 - p : p;
+        uint8_t *pd = dst + (size_t)p * plane_stride + (size_t)y0 * dpitch + (size_t)x0 * (OUTF ? 4 : 1);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { v[i] = clamp_i(c[ch][rr][i], SMAX); if (SBITS == 16) v[i] >>= 8; }
+            uint8_t *q = pd + (size_t)rr * dpitch;
+            if (OUTF) {
+                float *qf = reinterpret_cast<float *>(q);
+                if (full && ((((uintptr_t)dst | (uintptr_t)dpitch | (uintptr_t)plane_stride) & 15) == 0)) {
+                    __stcs(reinterpret_cast<float4 *>(qf), make_float4(tab[v[0]], tab[v[1]], tab[v[2]], tab[v[3]]));
+                    __stcs(reinterpret_cast<float4 *>(qf) + 1, make_float4(tab[v[4]], tab[v[5]], tab[v[6]], tab[v[7]]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) if (x0 + i < src.w && y0 + rr < src.h) qf[i] = tab[v[i]];
+                }
+            } else {
+                if (full && ((((uintptr_t)dst | (uintptr_t)dpitch | (uintptr_t)plane_stride) & 7) == 0)) {
+                    stg64(q, make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) if (x0 + i < src.w && y0 + rr < src.h) q[i] = (uint8_t)v[i];
+                }
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------
 // 8-sample / 4-sample vector row accesses (samples of 1 or 2 bytes)
@@ -718,6 +784,51 @@ static int launch_yuv2rgb_dst(int dc, dim3 g, cudaStream_t st, const Img &s, con
 #undef C
     default: return GMATB_ERR_UNSUPPORTED;
     }
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+int yuv2rgb_planar8_launch(const GmatbImage *src, uint8_t *dst, int dpitch, long long plane_stride, bool outf, bool swap,
+                           const Mat9 &M, cudaStream_t st) {
+    if (!src || !dst || src->width <= 0 || src->height <= 0) return GMATB_ERR_INVAL;
+    const bool b16 = src->format == GMATB_FMT_P016LE || src->format == GMATB_FMT_P010LE;
+    if (!b16 && src->format != GMATB_FMT_NV12) return GMATB_ERR_UNSUPPORTED;
+    Img s;
+    if (!to_img(src, &s, 2)) return GMATB_ERR_INVAL;
+    const bool sparse = (M.m[1] == 0.f && M.m[8] == 0.f);
+    const int vec = aligned16(s, 2);
+    dim3 g = tile_grid(s.w, s.h, 2, 1), b(32, 8);
+#define K4(B, F, W) do { if (sparse) yuv2rgb_planar8_kernel<B, F, W, true><<<g, b, 0, st>>>(s, dst, dpitch, plane_stride, M, vec); \
+                         else yuv2rgb_planar8_kernel<B, F, W, false><<<g, b, 0, st>>>(s, dst, dpitch, plane_stride, M, vec); } while (0)
+#define K3(B, F) do { if (swap) K4(B, F, true); else K4(B, F, false); } while (0)
+#define K2(B) do { if (outf) K3(B, true); else K3(B, false); } while (0)
+    if (b16) K2(16); else K2(8);
+#undef K2
+#undef K3
+#undef K4
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+// NV12 -> BGRA / RGBA / BGRA64 in the FMA form (metrans NvCodec/ColorSpace.cu: Nv12ToBgra32, Nv12ToRgba32, Nv12ToBgra64)
+int yuv2rgb_nv12_fma_launch(const GmatbImage *src, const GmatbImage *dst, const Mat9 &M, cudaStream_t st) {
+    if (!src || !dst || src->width != dst->width || src->height != dst->height || src->width <= 0 || src->height <= 0 ||
+        src->format != GMATB_FMT_NV12) return GMATB_ERR_INVAL;
+    const int dc = dst_code(dst->format);
+    Img s, d;
+    if (!to_img(src, &s, 2) || !to_img(dst, &d, 1)) return GMATB_ERR_INVAL;
+    const bool sparse = (M.m[1] == 0.f && M.m[8] == 0.f);
+    const int vec = aligned16(s, 2) && aligned16(d, 1);
+    dim3 g = tile_grid(s.w, s.h, 2, src->batch), b(32, 8);
+#define GO(D) do { if (sparse) yuv2rgb_kernel<L_NV12, 8, D, true, true><<<g, b, 0, st>>>(s, d, M, vec); \
+                   else yuv2rgb_kernel<L_NV12, 8, D, false, true><<<g, b, 0, st>>>(s, d, M, vec); } while (0)
+    switch (dc) {
+    case D_BGRA: GO(D_BGRA); break;
+    case D_RGBA: GO(D_RGBA); break;
+    case D_BGRA64: GO(D_BGRA64); break;
+    default: return GMATB_ERR_UNSUPPORTED;
+    }
+#undef GO
     count_launch();
     return set_cuda_error(cudaGetLastError());
 }
