@@ -88,3 +88,93 @@ def gather_frames(mine, frame_bytes, n_frames, root=0, device=None):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return full
+
+
+def bind_rank_to_cores(local_rank, local_world):
+    """Give every rank of a node its own slice of the host cores BEFORE it allocates pinned memory, so that the
+    staging buffers of the eight processes are first-touched (and their copy threads run) on distinct cores, inside
+    the CPU set NVML reports as local to the rank's GPU when that is known.  Returns the core list (or None)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    near = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+        near = [c for c in allowed if (words[c // 64] >> (c % 64)) & 1]
+    except Exception:
+        near = None
+    pool = near if near else allowed
+    per = max(1, len(pool) // max(local_world, 1))
+    mine = pool[(local_rank * per) % len(pool):][:per] or pool
+    try:
+        os.sched_setaffinity(0, set(mine))
+    except OSError:
+        return None
+    return mine
+
+
+def pipelined_scatter_compute_gather(full_in, in_frame_bytes, out_frame_bytes, n_frames, compute, chunk=8, root=0, device=None):
+    """SURVEY 8e report (2): the root rank holds the whole input batch; every rank receives its shard in chunks of
+    `chunk` frames, transforms chunk k while chunk k+1 is still arriving, and sends each result chunk back as soon
+    as it is ready.  Point-to-point only (NCCL send/recv over NVLink on GPUs, gloo on the CPU tests); `compute(src,
+    dst, nframes)` works on uint8 tensors.  Returns the full output on the root, None elsewhere."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    a, b = shard_range(n_frames, rank, world)
+    mine_n = b - a
+    if world == 1:
+        out = torch.empty(n_frames * out_frame_bytes, dtype=torch.uint8, device=full_in.device)
+        for c0 in range(0, n_frames, chunk):
+            n = min(chunk, n_frames - c0)
+            compute(full_in[c0 * in_frame_bytes:(c0 + n) * in_frame_bytes], out[c0 * out_frame_bytes:(c0 + n) * out_frame_bytes], n)
+        return out
+    dev = device if device is not None else (full_in.device if full_in is not None else None)
+    full_out = torch.empty(n_frames * out_frame_bytes, dtype=torch.uint8, device=dev) if rank == root else None
+    my_in = torch.empty(mine_n * in_frame_bytes, dtype=torch.uint8, device=dev) if rank != root else full_in[a * in_frame_bytes:b * in_frame_bytes]
+    my_out = torch.empty(mine_n * out_frame_bytes, dtype=torch.uint8, device=dev) if rank != root else full_out[a * out_frame_bytes:b * out_frame_bytes]
+    nchunks = (max(shard_range(n_frames, r, world)[1] - shard_range(n_frames, r, world)[0] for r in range(world)) + chunk - 1) // chunk
+    pending = []
+    # inputs: chunk-major, so that every rank gets its first chunk before anybody gets a second one
+    recv_in = []
+    for k in range(nchunks):
+        ops = []
+        if rank == root:
+            for r in range(world):
+                if r == root:
+                    continue
+                ra, rb = shard_range(n_frames, r, world)
+                f0, f1 = ra + k * chunk, min(ra + (k + 1) * chunk, rb)
+                if f1 > f0:
+                    ops.append(dist.P2POp(dist.isend, full_in[f0 * in_frame_bytes:f1 * in_frame_bytes], r))
+        else:
+            f0, f1 = k * chunk, min((k + 1) * chunk, mine_n)
+            if f1 > f0:
+                ops.append(dist.P2POp(dist.irecv, my_in[f0 * in_frame_bytes:f1 * in_frame_bytes], root))
+        recv_in.append(dist.batch_isend_irecv(ops) if ops else [])
+    # compute chunk k as soon as it is here; its result leaves while chunk k+1 is converted
+    for k in range(nchunks):
+        for w in recv_in[k]:
+            w.wait()
+        f0, f1 = k * chunk, min((k + 1) * chunk, mine_n)
+        if f1 > f0:
+            compute(my_in[f0 * in_frame_bytes:f1 * in_frame_bytes], my_out[f0 * out_frame_bytes:f1 * out_frame_bytes], f1 - f0)
+        ops = []
+        if rank == root:
+            for r in range(world):
+                if r == root:
+                    continue
+                ra, rb = shard_range(n_frames, r, world)
+                g0, g1 = ra + k * chunk, min(ra + (k + 1) * chunk, rb)
+                if g1 > g0:
+                    ops.append(dist.P2POp(dist.irecv, full_out[g0 * out_frame_bytes:g1 * out_frame_bytes], r))
+        elif f1 > f0:
+            ops.append(dist.P2POp(dist.isend, my_out[f0 * out_frame_bytes:f1 * out_frame_bytes], root))
+        if ops:
+            pending += dist.batch_isend_irecv(ops)
+    for w in pending:
+        w.wait()
+    return full_out

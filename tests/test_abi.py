@@ -31,6 +31,39 @@ def test_library_exports_everything_the_header_declares():
     assert L.gmatb_version() == 0x000100
 
 
+def test_nvcodec_header_and_cxx_dropin_symbols():
+    """include/gmat_b200_nvcodec.h: the C ABI is in libgmat_b200.so, the reference's own C++ signatures
+    (metrans/include/NvCodec/NvCommon.h:232-255, Itanium-mangled) in libgmat_b200_nvcodec.so"""
+    import gmat_b200
+    syms = exported(gmat_b200.lib_path())
+    for name in declared("gmat_b200_nvcodec.h"):
+        assert name in syms, name
+    cxx = exported(os.path.join(ROOT, "gmat_b200", "libgmat_b200_nvcodec.so"))
+    conv = ["Nv12ToBgra32", "Nv12ToRgba32", "Nv12ToBgra64", "P016ToBgra32", "P016ToBgra64", "Nv12ToBgrPlanar", "Nv12ToRgbPlanar",
+            "P016ToBgrPlanar", "Bgra64ToP016"]
+    for n in conv:
+        assert f"_Z{len(n)}{n}PhiS_iiiiP11CUstream_st" in cxx, n
+    for n in ("Nv12ToBgrFloatPlanar", "Nv12ToRgbFloatPlanar", "P016ToBgrFloatPlanar"):
+        assert f"_Z{len(n)}{n}PhiPfiiiiP11CUstream_st" in cxx, n
+    assert "_Z17ScaleNv12_BicubicPhiiiS_iii" in cxx
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_nvcodec.so")
+    if os.path.exists(ref):        # the reference's own objects export the same names (minus the texture-filter scalers)
+        r = exported(ref)
+        assert {s for s in cxx if s.startswith("_Z")} <= r
+
+
+def test_avfilter_harness_registers_the_six_filters():
+    """oracle/_ref/libref_avfilter.so = the reference's libavfilter + libavutil with our filter objects in filter_list.c"""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_avfilter.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/refbuild avf not built")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so]).decode()
+    for n in ("crop", "rotate", "flip", "smooth", "scale", "format"):
+        assert f"ff_vf_{n}_cuda" in out, n
+    for n in ("avfilter_graph_config", "av_buffersrc_add_frame", "av_hwframe_transfer_data", "avf_run"):
+        assert n in out, n
+
+
 def test_nine_libswscale_symbols_are_provided():
     import gmat_b200
     a = exported(gmat_b200.lib_path())

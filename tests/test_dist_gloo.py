@@ -65,3 +65,57 @@ def test_scatter_gather_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _pipe_worker(rank, world, port, n_frames, fin, fout, chunk, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gmat_b200.dist import pipelined_scatter_compute_gather
+    full = None
+    if rank == 0:
+        full = torch.arange(n_frames * fin, dtype=torch.int64).remainder(253).to(torch.uint8)
+    calls = []
+
+    def compute(src, dst, n):          # a per-frame transform that shrinks the frame (like 4K -> 1080p)
+        calls.append(n)
+        dst.copy_((src.view(n, fin)[:, :fout] ^ 0x5A).reshape(-1))
+    res = pipelined_scatter_compute_gather(full, fin, fout, n_frames, compute, chunk=chunk, root=0)
+    a, b = shard_range(n_frames, rank, world)
+    assert sum(calls) == b - a and all(c <= chunk for c in calls)
+    if rank == 0:
+        q.put(bool(torch.equal(res, (full.view(n_frames, fin)[:, :fout] ^ 0x5A).reshape(-1))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_scatter_compute_gather_world2_gloo():
+    """the chunked scatter -> transform -> gather pipeline of bench.py's NVLink end-to-end figure, on gloo"""
+    ctx = mp.get_context("spawn")
+    for n_frames, chunk in ((21, 4), (5, 8), (16, 8)):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_pipe_worker, args=(r, 2, port, n_frames, 600, 150, chunk, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert q.get(timeout=5) is True
+
+
+def test_bind_rank_to_cores_partitions_the_allowed_set():
+    from gmat_b200.dist import bind_rank_to_cores
+    before = os.sched_getaffinity(0)
+    try:
+        got = []
+        for r in range(4):
+            os.sched_setaffinity(0, before)          # every rank is its own process in real life
+            got.append(bind_rank_to_cores(r, 4))
+        os.sched_setaffinity(0, before)
+        got = [g for g in got if g]
+        assert got, "no affinity support"
+        assert all(set(g) <= before for g in got)
+        if len(before) >= 4:
+            assert len(set().union(*[set(g) for g in got])) == sum(len(g) for g in got)      # disjoint
+    finally:
+        os.sched_setaffinity(0, before)
