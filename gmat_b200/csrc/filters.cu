@@ -506,6 +506,22 @@ extern "C" int gmatb_rotate(const GmatbImage *src, const GmatbImage *dst, double
     if ((interp == GMATB_INTERP_LINEAR || interp == GMATB_INTERP_AREA) && d.w % 4 == 0 && s.w >= 2 &&
         (sal & 3) == 0 && (dal & (d.bpp == 3 ? 3 : 15)) == 0) {
         dim3 b4(8, 32), g4((d.w / 4 + 7) / 8, (d.h + 31) / 32, nbatch(src));
+        // TMA-staged gather: the bounding box of a 32 x 32 tile's footprint, + the tap, + slack for the word reads
+        {
+            const double ac = fabs(R.c), as = fabs(R.s);
+            const int ext = (int)ceil(31.0 * (ac + as)) + 4;
+            const unsigned box_x = (unsigned)((ext * d.bpp + 8 + 15 + 15) / 16 * 16), box_y = (unsigned)ext;   // + the 16-byte alignment of the origin
+            CUtensorMap tm;
+            if (s.w >= 64 && s.h >= 64 && box_x <= 256 && box_y <= 256 &&
+                make_tensor_map_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, s.p, (unsigned long long)s.w * s.bpp, s.h, nbatch(src), s.pitch,
+                                   nbatch(src) > 1 ? s.bstride : 0, box_x, box_y)) {
+                const size_t smem = (size_t)box_x * box_y;
+                if (d.bpp == 3) rotate_linear_tma_kernel<3><<<g4, b4, smem, (cudaStream_t)stream>>>(tm, s, d, R, (int)box_x, (int)box_y);
+                else            rotate_linear_tma_kernel<4><<<g4, b4, smem, (cudaStream_t)stream>>>(tm, s, d, R, (int)box_x, (int)box_y);
+                count_launch();
+                return set_cuda_error(cudaGetLastError());
+            }
+        }
         if (d.bpp == 3) rotate_linear4_kernel<3><<<g4, b4, 0, (cudaStream_t)stream>>>(s, d, R);
         else            rotate_linear4_kernel<4><<<g4, b4, 0, (cudaStream_t)stream>>>(s, d, R);
         count_launch();

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gmatb {
 
@@ -47,6 +48,34 @@ bool to_img(const GmatbImage *g, Img *out, int nplanes) {
         out->pl[i].bstride = g->batch > 1 ? g->batch_stride[i] : 0;
     }
     return true;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda)
+bool make_tensor_map_3d(CUtensorMap *out, CUtensorMapDataType dtype, int elem_bytes, const void *base, unsigned long long dim_x,
+                        unsigned long long dim_y, unsigned long long dim_z, unsigned long long pitch_bytes, unsigned long long frame_bytes,
+                        unsigned box_x, unsigned box_y) {
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+    static Encode enc = nullptr;
+    static std::atomic<int> state{0};          // 0 unknown, 1 ok, 2 unavailable
+    if (state.load() == 0) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn && q == cudaDriverEntryPointSuccess) {
+            enc = (Encode)fn; state.store(1);
+        } else state.store(2);
+    }
+    if (state.load() != 1) return false;
+    if (((uintptr_t)base & 15) || (pitch_bytes & 15) || (frame_bytes & 15) || box_x > 256 || box_y > 256 || ((box_x * elem_bytes) & 15)) return false;
+    if (dim_z < 1) dim_z = 1;
+    if (frame_bytes == 0) frame_bytes = pitch_bytes * dim_y;      // single frame: any legal stride
+    const cuuint64_t dims[3] = {dim_x, dim_y, dim_z};
+    const cuuint64_t strides[2] = {pitch_bytes, frame_bytes};
+    const cuuint32_t box[3] = {box_x, box_y, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(out, dtype, 3, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Same expressions, same types, same evaluation order as the reference

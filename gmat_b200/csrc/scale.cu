@@ -268,6 +268,7 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
 
 // exact-integer instantiations (8-bit yuv sources, dyadic weights): scale_int.cu
 int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
+int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -346,6 +347,8 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         launch_fused_t<L_RGB3, 8, D_RGB24>(c->taps2, wrap, g, c->stream, P);
         count_launch();
         rc = set_cuda_error(cudaGetLastError());
+    } else if (c->iw && semi && (c->flags & GMATB_SWS_MMA_CHAIN) && dc <= D_BGRA) {
+        rc = fused_mma_launch(dc, c->iw, wrap, g, c->stream, P);
     } else if (c->iw && (c->flags & GMATB_SWS_INT_CHAIN)) {
         rc = fused_int_launch(semi, dc, c->iw, wrap, g, c->stream, P);
     } else if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);

@@ -94,6 +94,9 @@ extern "C" {
  * applies (8-bit yuv sources, dyadic bicubic weights: param0 = 0.75, 0.5, 1.0).  Same output bytes as the default
  * float-chain kernel (tests/test_gpu_scale_int.py); measured slower on B200, hence opt-in. */
 #define GMATB_SWS_INT_CHAIN     0x20000000
+/* gmat_b200 extension bit: the same exact-integer chain with its horizontal pass on the tensor pipe (IMMA u8 x s8,
+ * scale_fused5m.cuh); NV12 sources, 8-bit packed rgb destinations, same dyadic weights, same output bytes. */
+#define GMATB_SWS_MMA_CHAIN     0x10000000
 
 /* ---- interpolation / border codes of the filter layer (NVCV numbering:
  *      NVCV_INTERP_* / NVCV_BORDER_* as used by vf_rotate_nvcv.c:115-135 and

@@ -54,14 +54,15 @@ def content(fb, kind, seed):
     return host
 
 
-def run_pair(dev, sfmt, dfmt, sw, sh, n, kind, param, wrap, seed=1):
+def run_pair(dev, sfmt, dfmt, sw, sh, n, kind, param, wrap, seed=1, chain=None):
+    chain = SWS.INT_CHAIN if chain is None else chain
     dw, dh = sw // 2, sh // 2
     src = FrameBatch(sfmt, sw, sh, n)
     host = content(src, kind, seed)
     src.upload(host)
     ds = src.to(dev)
     fl = SWS.BICUBIC | HW | (SWS.PARITY_WRAP if wrap else 0)
-    ci = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.INT_CHAIN, param)
+    ci = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | chain, param)
     cf = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl, param)
     assert ci.path == 1 and cf.path == 1
     a = FrameBatch(dfmt, dw, dh, n, device=dev); b = FrameBatch(dfmt, dw, dh, n, device=dev)
@@ -103,3 +104,32 @@ def test_int_selected_only_for_dyadic_weights(dev):
     for param in ((0.6,), (0.3,), None):
         _, _, a, b = run_pair(dev, FMT.NV12, FMT.RGB24, 512, 130, 1, "noise", param, False)
         assert torch.equal(a.buf, b.buf)
+
+
+# ---- the tensor-pipe form (scale_fused5m.cuh, SWS.MMA_CHAIN): NV12 sources, horizontal pass on IMMA ----------------------
+@pytest.mark.parametrize("kind", CONTENT)
+@pytest.mark.parametrize("param", PARAMS)
+@pytest.mark.parametrize("sw,sh", [(64, 48), (16, 4), (8, 2), (512, 130), (240, 12), (248, 140), (488, 66), (1920, 1080), (3848, 34)])
+def test_mma_equals_float_chain(dev, kind, param, sw, sh):
+    for dfmt, wrap in ((FMT.RGB24, False), (FMT.BGRA, True), (FMT.BGR24, True), (FMT.RGBA, False)):
+        _, _, a, b = run_pair(dev, FMT.NV12, dfmt, sw, sh, 2, kind, param, wrap, seed=sw + sh, chain=SWS.MMA_CHAIN)
+        if not torch.equal(a.buf, b.buf):
+            assert_same(a, b, f"mma vs float chain {kind} {param} NV12->{dfmt} wrap={wrap} {sw}x{sh}")
+
+
+@pytest.mark.parametrize("kind", ["noise", "patches", "halfflat", "stripes", "lowamp"])
+@pytest.mark.parametrize("param", PARAMS)
+def test_mma_vs_oracle(dev, kind, param):
+    """the tensor-pipe kernel against the CPU restatement of the reference's float chain"""
+    for dfmt in (FMT.RGB24, FMT.BGRA):
+        src, ci, a, _ = run_pair(dev, FMT.NV12, dfmt, 264, 72, 2, kind, param, False, seed=5, chain=SWS.MMA_CHAIN)
+        ref = FrameBatch(dfmt, 132, 36, 2)
+        orc.yuv2rgb_scale(src, ref, (ci.get_filter(0), ci.get_filter(1)))
+        assert_same(a, ref, f"mma kernel vs oracle {kind} {param} NV12->{dfmt}")
+
+
+@pytest.mark.parametrize("kind", ["noise", "patches", "halfflat", "leftflat", "flat", "stripes"])
+def test_mma_headline_4k(dev, kind):
+    """BASELINE C2 at full size, 3 frames"""
+    _, _, a, b = run_pair(dev, FMT.NV12, FMT.RGB24, 3840, 2160, 3, kind, (0.75,), False, seed=11, chain=SWS.MMA_CHAIN)
+    assert torch.equal(a.buf, b.buf), f"4K {kind}: {(a.buf != b.buf).sum().item()} bytes differ"

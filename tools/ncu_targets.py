@@ -12,6 +12,8 @@ d720 = FrameBatch(FMT.RGB24, 1280, 720, B, device=dev)
 which = sys.argv[1:] or ["fused", "bilinear", "generic", "rotate", "gauss", "median", "rgb2yuv", "fliph"]
 if "fused" in which:
     SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | HW, (0.75,)).scale(src, d1080)
+if "fused_mma" in which:
+    SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | SWS.MMA_CHAIN | HW, (0.75,)).scale(src, d1080)
 if "fused_default" in which:
     SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.RGB24, SWS.BICUBIC | HW).scale(src, d1080)
 if "c3" in which:

@@ -25,5 +25,6 @@ def run(label, flags, param):
 for kind in ("noise", "flat", "half"):
     fill(kind)
     for p in ((0.75,), (0.5,)):
-        run(f"{kind} int   param {p}", SWS.BICUBIC | SWS.INT_CHAIN, p)
+        run(f"{kind} mma   param {p}", SWS.BICUBIC | SWS.MMA_CHAIN, p)
+        if os.environ.get("PERF_INT"): run(f"{kind} int   param {p}", SWS.BICUBIC | SWS.INT_CHAIN, p)
         run(f"{kind} float param {p}", SWS.BICUBIC, p)
