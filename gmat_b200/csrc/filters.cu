@@ -592,7 +592,7 @@ extern "C" int gmatb_gaussian(const GmatbImage *src, const GmatbImage *dst, int 
         S.band = (d.h + bands - 1) / bands;
         bands = (d.h + S.band - 1) / S.band;
         dim3 g2((wx + 127) / 128, bands, nb);
-        const int minb = 5;
+        const int minb = d.bpp == 4 ? 4 : 5;        // 4: 128 registers, loads two rows ahead (gauss_stream.cuh)
 #define GS(B, KW_, KH_) do { if (minb >= 5) gauss_stream_kernel<B, KW_, KH_, 5><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); \
         else gauss_stream_kernel<B, KW_, KH_, 4><<<g2, 128, 0, st>>>(s.p, s.pitch, s.bstride, d.p, d.pitch, d.bstride, d.h, t0, t1, S); } while (0)
 #define GK(B, KW_) do { if (kh == 3) GS(B, KW_, 3); else if (kh == 5) GS(B, KW_, 5); else GS(B, KW_, 7); } while (0)
