@@ -454,7 +454,8 @@ def main():
                               "achieved_gbs_per_gpu": salg / (m * 1e-3) / 1e9, "frac": salg / (m * 1e-3) / 1e9 / peak})
         for label, fl, par in (("C2 frames, default bicubic parameter (A=0)", SWS.BICUBIC, None),
                                ("C2 frames, SWS_BILINEAR (what the reference really runs for every flag, R-A arithmetic)", SWS.BILINEAR, None),
-                               ("C2 frames, exact-integer form of the headline kernel (SWS.INT_CHAIN, same bytes)", SWS.BICUBIC | SWS.INT_CHAIN, (0.75,))):
+                               ("C2 frames, exact-integer form of the headline kernel (SWS.INT_CHAIN, same bytes)", SWS.BICUBIC | SWS.INT_CHAIN, (0.75,)),
+                               ("C2 frames, tensor-pipe form of the headline kernel (SWS.MMA_CHAIN: horizontal pass on IMMA u8 x s8, same bytes)", SWS.BICUBIC | SWS.MMA_CHAIN, (0.75,))):
             c2 = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.HWACCEL_CUDA, par)
             sec(label, lambda c2=c2: c2.scale(src, dst), px, alg_bytes_launch)
         f4, p4, a4, d4 = c4_workload(dev, max(1, 256 // max(world, 8)))      # BASELINE configs[3]: batch 256 over 8 GPUs

@@ -9,6 +9,7 @@
 #include "scale_fused3.cuh"
 #include "scale_bilinear2.cuh"
 #include "scale_generic.cuh"
+#include "scale_stream.cuh"
 
 namespace gmatb {
 int yuv2rgb_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, cudaStream_t);
@@ -76,6 +77,8 @@ struct GmatbSws {
     float wx[4], wy[4];
     bool taps2;
     int iw;   // 0, or 1..3: both axes have the dyadic weights of the exact-integer kernel (scale_fused4i.cuh)
+    // any-ratio streaming kernel (scale_stream.cuh): which strip / outputs each warp owns; built on first use
+    int4 *splan; int splan_n, splan_nout, splan_state;   // state: 0 not built, 1 ready, -1 does not apply
     // scratch
     void *tmp; size_t tmp_size;
     void *stage_src, *stage_dst; size_t stage_src_size, stage_dst_size;
@@ -120,6 +123,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
     c->tmp = c->stage_src = c->stage_dst = nullptr;
     c->tmp_size = c->stage_src_size = c->stage_dst_size = 0;
     c->pipe = nullptr;
+    c->splan = nullptr; c->splan_n = c->splan_nout = c->splan_state = 0;
     c->srcW = srcW; c->srcH = srcH; c->srcFmt = srcFormat; c->dstW = dstW; c->dstH = dstH; c->dstFmt = dstFormat;
     c->flags = flags; c->cspace = colorspace; c->stream = 0;
     c->param[0] = param ? param[0] : GMATB_SWS_PARAM_DEFAULT;
@@ -201,7 +205,7 @@ extern "C" void gmatb_sws_free(GmatbSws *c) {
     for (int i = 0; i < 2; i++) {
         cudaFree(c->cx[i]); cudaFree(c->cy[i]); cudaFree(c->px[i]); cudaFree(c->py[i]);
     }
-    cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst);
+    cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst); cudaFree(c->splan);
     host_pipe_free(c->pipe);
     delete c;
 }
@@ -269,6 +273,8 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
 // exact-integer instantiations (8-bit yuv sources, dyadic weights): scale_int.cu
 int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
+// any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
+int stream_launch(bool semi, int dc, int nout, dim3 g, cudaStream_t st, const StreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -353,6 +359,82 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
         rc = fused_int_launch(semi, dc, c->iw, wrap, g, c->stream, P);
     } else if (semi) rc = bits == 8 ? launch_fused_d<L_NV12, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_NV12, 16>(dc, c->taps2, wrap, g, c->stream, P);
     else      rc = bits == 8 ? launch_fused_d<L_I420, 8>(dc, c->taps2, wrap, g, c->stream, P) : launch_fused_d<L_I420, 16>(dc, c->taps2, wrap, g, c->stream, P);
+    *done = (rc == 0);
+    return rc;
+}
+
+// The warps of the streaming kernel: greedy cut of the output columns.  A warp converts source columns [X0, X0 + 8 lanes)
+// (X0 a multiple of 8, at most 256 columns) and owns outputs [xo, xo + n): every tap of every owned output, clamped to the
+// frame, must lie in its strip (taps left of column 0 / right of column W-1 are the replicated pad entries).
+static bool build_stream_plan(GmatbSws *c) {
+    const std::vector<int> &px = c->hpx[0];
+    const int W = c->srcW, dW = c->dstW;
+    if (W < 16 || c->srcH < 2 || dW < 1 || (int)px.size() != dW) return false;
+    const double r = (double)W / dW;
+    if (r > 48.0) return false;
+    const int nout = r >= 2.5 ? 3 : 5;
+    std::vector<int4> plan;
+    int xo = 0;
+    while (xo < dW) {
+        const int X0 = std::max(px[xo], 0) & ~7;
+        int n = 0, last = X0;
+        const int cap = std::min(32 * nout, dW - xo);
+        while (n < cap) {
+            const int right = std::min(px[xo + n] + 3, W - 1);
+            if (right > X0 + 255) break;
+            last = std::max(last, right);
+            n++;
+        }
+        if (xo + n < dW) n &= ~3;                 // every warp but the last starts the next one on a multiple of 4
+        if (n <= 0) return false;
+        last = X0;
+        for (int i = 0; i < n; i++) last = std::max(last, std::min(px[xo + i] + 3, W - 1));
+        plan.push_back(make_int4(X0, xo, n, (last - X0) / 8 + 1));
+        xo += n;
+    }
+    if (cudaMalloc(&c->splan, plan.size() * sizeof(int4)) != cudaSuccess) return false;
+    if (cudaMemcpy(c->splan, plan.data(), plan.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    c->splan_n = (int)plan.size(); c->splan_nout = nout;
+    return true;
+}
+
+// 8-bit yuv 4:2:0 -> 8-bit packed rgb at any ratio, R-B arithmetic: the streaming kernel
+static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
+    *done = false;
+    if (c->splan_state < 0) return 0;
+    const int dc = rgb_dst_code(dst->format);
+    if (c->ra || fmt_bits(src->format) != 8 || dc < 0 || dc > D_BGRA || !(c->M.m[1] == 0.f && c->M.m[8] == 0.f)) { c->splan_state = -1; return 0; }
+    if (c->splan_state == 0) {
+        if (!build_stream_plan(c)) { c->splan_state = -1; return 0; }
+        c->splan_state = 1;
+    }
+    StreamParams P;
+    memset(&P, 0, sizeof(P));
+    const int np = fmt_planes(src->format);
+    if (!to_img(src, &P.F.src, np) || !to_img(dst, &P.F.dst, 1)) return GMATB_ERR_INVAL;
+    const bool semi = np == 2;
+    if (!planes_aligned(P.F.src, 1, 8) || (semi ? !planes_aligned(P.F.src, 2, 8) : !planes_aligned(P.F.src, 3, 4))) return 0;
+    if (!planes_aligned(P.F.dst, 1, 4)) return 0;
+    // the last chunk of a row is read whole: the pitch must cover it
+    if (P.F.src.pl[0].pitch < ((c->srcW + 7) & ~7)) return 0;
+    if (semi ? P.F.src.pl[1].pitch < ((c->srcW + 7) & ~7) : (P.F.src.pl[1].pitch < ((c->srcW + 7) & ~7) / 2 || P.F.src.pl[2].pitch < ((c->srcW + 7) & ~7) / 2)) return 0;
+    P.F.cm45[0] = c->M.m[4]; P.F.cm45[1] = c->M.m[5]; P.F.cm72[0] = c->M.m[7]; P.F.cm72[1] = c->M.m[2];
+    P.F.m0 = c->M.m[0]; P.F.m1 = c->M.m[1]; P.F.m3 = c->M.m[3]; P.F.m6 = c->M.m[6];
+    P.F.nk = norm_k(8);
+    P.F.factor = 255.f;
+    P.F.dstW = c->dstW; P.F.dstH = c->dstH;
+    P.cx = c->cx[0]; P.cy = c->cy[0]; P.px = c->px[0]; P.py = c->py[0];
+    P.plan = c->splan;
+    P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
+    const int batch = src->batch > 1 ? src->batch : 1;
+    // bands: enough warps for a few waves of 148 SMs x 12-16 resident warps, no shorter than 16 output rows
+    long long want = 148LL * 16 * 6;
+    int nb = (int)((want + (long long)c->splan_n * batch - 1) / ((long long)c->splan_n * batch));
+    nb = std::max(1, std::min(nb, (c->dstH + 15) / 16));
+    P.band = (c->dstH + nb - 1) / nb;
+    nb = (c->dstH + P.band - 1) / P.band;
+    dim3 g(c->splan_n, nb, batch);
+    int rc = stream_launch(semi, dc, c->splan_nout, g, c->stream, P);
     *done = (rc == 0);
     return rc;
 }
@@ -513,6 +595,11 @@ static int scale_batch(GmatbSws *c, const GmatbImage *src_in, const GmatbImage *
         if (c->path == PATH_FUSED2) {
             bool done = false;
             int rc = run_fused(c, &src, &dst, &done);
+            if (rc || done) return rc;
+        }
+        if (!(c->flags & GMATB_SWS_TILE_KERNEL)) {
+            bool done = false;
+            int rc = run_stream(c, &src, &dst, &done);
             if (rc || done) return rc;
         }
         Img s, d;

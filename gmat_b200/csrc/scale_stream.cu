@@ -1,0 +1,31 @@
+// scale_stream.cu -- instantiations and launcher of the any-ratio streaming kernel (scale_stream.cuh); its own
+// translation unit so that it builds in parallel with scale.cu.
+#include "scale_generic.cuh"
+#include "scale_stream.cuh"
+
+namespace gmatb {
+
+template <int L, int DST>
+static void launch_stream_t(int nout, dim3 g, cudaStream_t st, const StreamParams &P) {
+    // NOUT = outputs per lane: 3 (ratios >= 2.5: at most 96 outputs per 240-column strip) or 5
+    if (nout <= 3) fused_csc_scale_stream_kernel<L, DST, 3, 16><<<g, 32, 0, st>>>(P);
+    else           fused_csc_scale_stream_kernel<L, DST, 5, 12><<<g, 32, 0, st>>>(P);
+}
+template <int L>
+static int launch_stream_d(int dc, int nout, dim3 g, cudaStream_t st, const StreamParams &P) {
+    switch (dc) {
+    case D_RGB24: launch_stream_t<L, D_RGB24>(nout, g, st, P); break;
+    case D_BGR24: launch_stream_t<L, D_BGR24>(nout, g, st, P); break;
+    case D_RGBA:  launch_stream_t<L, D_RGBA>(nout, g, st, P); break;
+    case D_BGRA:  launch_stream_t<L, D_BGRA>(nout, g, st, P); break;
+    default: return GMATB_ERR_UNSUPPORTED;
+    }
+    count_launch();
+    return set_cuda_error(cudaGetLastError());
+}
+
+int stream_launch(bool semi, int dc, int nout, dim3 g, cudaStream_t st, const StreamParams &P) {
+    return semi ? launch_stream_d<L_NV12>(dc, nout, g, st, P) : launch_stream_d<L_I420>(dc, nout, g, st, P);
+}
+
+}  // namespace gmatb

@@ -1,0 +1,236 @@
+// scale_stream.cuh -- ANY-RATIO fused colour conversion + 4-tap resample for 8-bit yuv 4:2:0 -> 8-bit packed rgb
+// (R-B arithmetic: bicubic / Lanczos; every ratio that is not the exact 2:1 of scale_fused3.cuh: 1080p -> 720p,
+// 4K -> 720p, 1080p -> 4K ...).  Same operations, in the same order, as the generic tile kernel
+// (scale_generic.cuh) and the reference's two-kernel pipeline (csc_core.cuh, resample_core.cuh): bit-identical.
+//
+// The generic kernel stages a destination tile's whole source window in shared memory as floats (three
+// stages, two CTA barriers, ~165 B of shared-memory traffic per destination pixel at 1.5:1) and ran at 6-11 % of
+// the HBM roofline.  Here the VERTICAL direction streams through registers like the 2:1 kernel, and shared memory
+// holds ONE row pair of converted samples, only to give the horizontal taps their run-time offsets:
+//   * one warp per CTA owns a strip of up to 256 source columns and walks down a band of the frame one row PAIR
+//     (one chroma row) per step; lane l loads and converts columns 8l .. 8l+7 of both rows exactly as
+//     scale_fused3.cuh does (64-bit loads two steps ahead, packed (top, bottom) CSC, quantise + normalise);
+//   * the 8 x 3 packed samples go to a 264-entry row buffer per channel (STS.128; entry = column - X0 + 2, two
+//     replicated entries on either side of the frame stand for the clamped taps), __syncwarp;
+//   * horizontal pass: the warp's outputs are dealt to the lanes round robin (output lane + 32 i, i < NOUT); each
+//     takes its 4 consecutive taps per channel from the row buffer at the offset of its column (one LDS.64 per
+//     tap: top and bottom row together) and runs the packed chain with its own 4 weights (registers);
+//   * vertical pass: the horizontal results of the 3 previous source rows stay in registers; every output row whose
+//     window ends at one of the two rows just produced is finished on the spot: 4-tap chain, scale, truncate, pack;
+//   * stores: rgba one word per lane; rgb24: the four pixels of a lane quad are re-dealt into three words with one
+//     SHFL + one PRMT, 96 contiguous bytes per warp store.
+// Which source strip and which outputs a warp owns is planned on the host (run_stream in scale.cu) from the
+// same position table the kernel's taps come from: first output a multiple of 4, strip start a multiple of 8.
+#pragma once
+#include <type_traits>
+#include "scale_fused3.cuh"
+
+namespace gmatb {
+
+#define GMATB_STREAM_BUF 264        /* entries per channel of the row buffer */
+
+struct StreamParams {
+    Fused3Params F;                 // images, matrix, normalisation constants (wx / wy / band unused)
+    const float4 *cx, *cy;          // per output column / row: the 4 weights
+    const int *px, *py;             // per output column / row: position of the first tap
+    const int4 *plan;               // per warp: x = first source column X0, y = first output column, z = outputs, w = converting lanes
+    int band;                       // output rows per CTA
+    int wrap;
+};
+
+static __device__ __noinline__ void stream_store_px3(uint8_t *pp, uint32_t pw) {
+    pp[0] = (uint8_t)pw; pp[1] = (uint8_t)(pw >> 8); pp[2] = (uint8_t)(pw >> 16);
+}
+
+template <int L, int DST, int NOUT, int MINB>
+__global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const __grid_constant__ StreamParams P) {
+    typedef Raw3<L, 8> Row;
+    constexpr int BPP = dst_bpp(DST);
+    constexpr bool SW = dst_swap(DST);
+    __shared__ __align__(16) f2 buf[3][GMATB_STREAM_BUF];
+    const int lane = threadIdx.x;
+    const long long fz = blockIdx.z;
+    const Fused3Params &F = P.F;
+    const int W = F.src.w, H = F.src.h, HC = (H + 1) >> 1;
+    const int4 pl = P.plan[blockIdx.x];
+    const int X0 = pl.x, xoA = pl.y, nout = pl.z, nconv = pl.w;
+
+    // ---- this lane's outputs: columns xoA + lane + 32 i -------------------------------------------------------
+    float4 wx[NOUT];
+    int off[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; i++) {
+        const int xo = xoA + min(lane + 32 * i, nout - 1);
+        wx[i] = __ldg(P.cx + xo);
+        off[i] = __ldg(P.px + xo) - X0 + 2;
+    }
+    const int yo_begin = blockIdx.y * P.band, yo_end = min(yo_begin + P.band, F.dstH);
+    const int v_first = __ldg(P.py + yo_begin), v_last = __ldg(P.py + yo_end - 1) + 3;
+    const int kp_start = v_first >> 1, kp_last = v_last >> 1;             // row pairs kp_start .. kp_last
+
+    // ---- source rows: this lane's 8 columns -------------------------------------------------------------------
+    const int cs = min(X0 + 8 * lane, (W - 1) & ~7);                     // lanes past the row end re-read its last chunk (never tapped)
+    const uint8_t *py_ = F.src.pl[0].p + fz * F.src.pl[0].bstride + cs;
+    const uint8_t *pu = F.src.pl[1].p + fz * F.src.pl[1].bstride + (L == L_NV12 ? cs : cs >> 1);
+    const uint8_t *pv = L == L_I420 ? F.src.pl[2].p + fz * F.src.pl[2].bstride + (cs >> 1) : pu;
+    const unsigned pitch_y = F.src.pl[0].pitch, pitch_c = F.src.pl[1].pitch, pitch_c2 = F.src.pl[2].pitch;
+    auto load_pair = [&](int kp, Row &R) {       // rows 2kp, 2kp+1 and chroma row kp, each clamped to the frame
+        const unsigned rt = (unsigned)min(max(2 * kp, 0), H - 1), rb = (unsigned)min(max(2 * kp + 1, 0), H - 1);
+        const unsigned rc = (unsigned)min(max(kp, 0), HC - 1);
+        R.yt = ldg64(py_ + rt * pitch_y); R.yb = ldg64(py_ + rb * pitch_y);
+        if (L == L_NV12) R.c0 = ldg64(pu + rc * pitch_c);
+        else { R.c0.x = ldg32(pu + rc * pitch_c); R.c0.y = ldg32(pv + rc * pitch_c2); }
+    };
+
+    // ---- destination ------------------------------------------------------------------------------------------
+    const unsigned pitch_d = F.dst.pl[0].pitch;
+    uint8_t *pd0 = F.dst.pl[0].p + fz * F.dst.pl[0].bstride + (size_t)xoA * BPP;
+    const int wmask = P.wrap ? 0xFF : 0x7fffffff;      // GMATB_SWS_PARITY_WRAP: values >= 256 wrap instead of saturating
+    // rgb24: lane q of a quad stores word q of the quad's 12 bytes (q < 3): bytes from its own pixel and the next lane's
+    const int q = lane & 3;
+    const uint32_t selq = q == 0 ? 0x4210u : q == 1 ? 0x5421u : 0x6542u;
+    // alpha of 4-channel outputs: the chain over the constant 255 the reference's CSC writes, p = 1.0 (scale_generic.cuh)
+    float ah[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; i++) ah[i] = gen_chain(wx[i].x, wx[i].y, wx[i].z, wx[i].w, 1.0f, 1.0f, 1.0f, 1.0f);
+
+    // horizontal results of the three source rows before the current pair, oldest first.  (They move down by two rows
+    // per step with register copies: with compile-time ring slots instead the step exists in four variants and the
+    // loop, 46 KB of code, thrashed the 32 KB instruction cache: 1.4 no-instruction stalls per issue under ncu.)
+    float hist[3][NOUT][3];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) { hist[s][i][0] = 0.f; hist[s][i][1] = 0.f; hist[s][i][2] = 0.f; }
+
+    // the next two output rows' window ends and weights (warp-uniform loads, issued well ahead of their use)
+    int yo = yo_begin;
+    int pend0 = v_first + 3, pend1 = yo + 1 < yo_end ? __ldg(P.py + yo + 1) + 3 : 0x7fffffff;
+    float4 wy0 = __ldg(P.cy + yo), wy1 = __ldg(P.cy + min(yo + 1, yo_end - 1));
+
+    // finish output row yo: its window is rows r0 (oldest) .. r3 (newest)
+    auto emit = [&](const float (&r0)[NOUT][3], const float (&r1)[NOUT][3], const float (&r2)[NOUT][3], const float (&r3)[NOUT][3]) {
+        const float4 w = wy0;
+        uint8_t *prow = pd0 + (size_t)yo * pitch_d;
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) {
+            int o[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float t = gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
+                // fmaxf(NaN, -1) = -1: a NaN (0/0 Lanczos coefficients, scale_generic.cuh) stores 0 like cvt.rzi.u32.f32
+                o[c] = max(trunc_i(fmaxf(__fmul_rn(t, F.factor), -1.0f)), 0) & wmask;    // the pack saturates the rest
+            }
+            int a = 255;
+            if (BPP == 4) {
+                const float av = gen_chain(w.x, w.y, w.z, w.w, ah[i], ah[i], ah[i], ah[i]);
+                a = max(trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f)), 0) & wmask;
+            }
+            const int oi = lane + 32 * i;                              // index of the pixel among the warp's outputs
+            const uint32_t pw = pack4_u8(SW ? o[2] : o[0], o[1], SW ? o[0] : o[2], a);      // saturating
+            if (BPP == 4) {
+                if (oi < nout) stg32(prow + (size_t)oi * 4, pw);
+            } else {
+                const uint32_t nx = __shfl_down_sync(0xffffffffu, pw, 1);
+                const int qb = oi & ~3;                                // first pixel of the quad
+                if (qb + 3 < nout) {
+                    if (q < 3) stg32(prow + (size_t)qb * 3 + 4 * q, prmt(pw, nx, selq));
+                } else if (oi < nout) stream_store_px3(prow + (size_t)oi * 3, pw);      // ragged last quad of the frame's last warp
+            }
+        }
+        ++yo;
+        pend0 = pend1; wy0 = wy1;
+        if (yo + 1 < yo_end) { pend1 = __ldg(P.py + yo + 1) + 3; wy1 = __ldg(P.cy + yo + 1); }
+        else pend1 = 0x7fffffff;
+    };
+
+    // Bank conflicts: a lane's 8 entries are 64 B, so the STS.128 of column pair j would hit 2 bank groups from the 8 lanes
+    // of a quarter warp (4-way conflict).  Lane l therefore works through its column pairs in the order j + rot (mod 4),
+    // rot = (l >> 1) & 3 -- its raw words are rotated by 2 rot bytes once per step, nothing else changes -- which puts
+    // the 8 stores of a quarter warp into 8 different bank groups.
+    const int rot = (lane >> 1) & 3;
+    f2 *wpos[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) wpos[j] = &buf[0][8 * lane + 2 + 2 * ((j + rot) & 3)];
+    const bool lpad = X0 == 0, rpad = X0 + 8 * nconv >= W;             // warp-uniform: the strip touches the frame's left / right edge
+    const f2 k45 = *reinterpret_cast<const f2 *>(F.cm45), k72 = *reinterpret_cast<const f2 *>(F.cm72);
+    constexpr float CB = -(GMATB_MAGIC + 128.f), YB = -(GMATB_MAGIC + 16.f);
+
+    // one row pair kp: convert, publish, horizontal pass, the output rows that end in it
+    auto step = [&](const Row &now, int kp) {
+        RawRow<8> rr;
+        {
+            auto rot64 = [&](uint2 v, int bits) {           // rotate the 8 bytes right by `bits` (0, 16, 32, 48)
+                const uint32_t lo = (bits & 32) ? v.y : v.x, hi = (bits & 32) ? v.x : v.y;
+                return make_uint2(__funnelshift_r(lo, hi, bits & 31), __funnelshift_r(hi, lo, bits & 31));
+            };
+            rr.yt = rot64(now.yt, 16 * rot); rr.yb = rot64(now.yb, 16 * rot);
+            if (L == L_NV12) rr.c0 = rot64(now.c0, 16 * rot);
+            else rr.c0 = make_uint2(__funnelshift_r(now.c0.x, now.c0.x, 8 * rot), __funnelshift_r(now.c0.y, now.c0.y, 8 * rot));
+        }
+        float yt[8], yb[8], um[4], vm[4];
+        fused_unpack<L>(rr, yt, yb, um, vm);
+        __syncwarp();                                  // the previous step's taps have been read
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                  // two columns (one chroma sample) at a time, published at once
+            const f2 uv = add2(pk(um[j], vm[j]), bc(CB));
+            float t1g, t2g, t1b, t2r;
+            upk(mul2(uv, k45), t1g, t2g);
+            upk(mul2(uv, k72), t1b, t2r);
+            f2 S[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = 2 * j + h;
+                const f2 fy2 = add2(pk(yt[col], yb[col]), bc(YB));
+                f2 xr = fma2(fy2, bc(F.m0), bc(F.m1));      // m1 is a run-time 0.0f: RN(fy*m0), as FFMA(fy, m0, +-0)
+                f2 xg = fma2(fy2, bc(F.m3), bc(t1g));
+                const f2 xb = fma2(fy2, bc(F.m6), bc(t1b));
+                xr = add2(xr, bc(t2r)); xg = add2(xg, bc(t2g));
+                S[h][0] = quant_norm2(xr, F.nk); S[h][1] = quant_norm2(xg, F.nk); S[h][2] = quant_norm2(xb, F.nk);
+            }
+            if (lane < nconv) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    *reinterpret_cast<ulonglong2 *>(wpos[j] + c * GMATB_STREAM_BUF) = make_ulonglong2(S[0][c], S[1][c]);
+                if (lpad && lane == 0 && j == 0) {           // lane 0 has rot = 0: this is column 0
+#pragma unroll
+                    for (int c = 0; c < 3; c++) *reinterpret_cast<ulonglong2 *>(&buf[c][0]) = make_ulonglong2(S[0][c], S[0][c]);
+                }
+            }
+        }
+        __syncwarp();
+        if (rpad) {                                    // columns W, W+1 = column W-1
+            if (lane < 3) { const f2 e = buf[lane][W - 1 - X0 + 2]; buf[lane][W - X0 + 2] = e; buf[lane][W - X0 + 3] = e; }
+            __syncwarp();
+        }
+        // ---- horizontal pass -------------------------------------------------------------------------------------
+        float htop[NOUT][3], hbot[NOUT][3];
+#pragma unroll
+        for (int i = 0; i < NOUT; i++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const f2 *t = &buf[c][off[i]];
+                const f2 hh = gen_chain2(wx[i].x, wx[i].y, wx[i].z, wx[i].w, t[0], t[1], t[2], t[3]);
+                upk(hh, htop[i][c], hbot[i][c]);
+            }
+        // ---- vertical pass: output rows whose window ends at row 2kp, then at row 2kp+1 ----------------------------
+        while (pend0 == 2 * kp) emit(hist[0], hist[1], hist[2], htop);
+        while (pend0 == 2 * kp + 1) emit(hist[1], hist[2], htop, hbot);
+#pragma unroll
+        for (int i = 0; i < NOUT; i++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { hist[0][i][c] = hist[2][i][c]; hist[1][i][c] = htop[i][c]; hist[2][i][c] = hbot[i][c]; }
+    };
+
+    // rows are loaded one pair ahead: the copy at the end of a step is the first use of the loaded words
+    Row cur, nxt;
+    load_pair(kp_start, cur);
+#pragma unroll 1
+    for (int kp = kp_start; kp <= kp_last; kp++) {
+        if (kp < kp_last) load_pair(kp + 1, nxt);
+        step(cur, kp);
+        cur = nxt;
+    }
+}
+
+}  // namespace gmatb

@@ -32,7 +32,7 @@ FMT = _NS(YUV420P=0, RGB24=2, BGR24=3, NV12=23, RGBA=26, BGRA=28, RGB48LE=35, YU
           P010LE=159, P016LE=170, RGBPF32LE=179, RGBAPF32LE=180)
 SPC = _NS(DEFAULT=0, BT709=1, FCC=4, BT470BG=5, SMPTE170M=6, SMPTE240M=7, BT2020_NCL=9, BT2020_CL=10)
 SWS = _NS(FAST_BILINEAR=1, BILINEAR=2, BICUBIC=4, POINT=0x10, AREA=0x20, LANCZOS=0x200,
-          HWACCEL_CUDA=0x1000000, PARITY_WRAP=0x40000000, INT_CHAIN=0x20000000, MMA_CHAIN=0x10000000, PARAM_DEFAULT=123456.0)
+          HWACCEL_CUDA=0x1000000, PARITY_WRAP=0x40000000, INT_CHAIN=0x20000000, MMA_CHAIN=0x10000000, TILE_KERNEL=0x08000000, PARAM_DEFAULT=123456.0)
 INTERP = _NS(NEAREST=0, LINEAR=1, CUBIC=2, AREA=3)
 BORDER = _NS(CONSTANT=0, REPLICATE=1, REFLECT=2, WRAP=3, REFLECT101=4)
 

@@ -97,6 +97,9 @@ extern "C" {
 /* gmat_b200 extension bit: the same exact-integer chain with its horizontal pass on the tensor pipe (IMMA u8 x s8,
  * scale_fused5m.cuh); NV12 sources, 8-bit packed rgb destinations, same dyadic weights, same output bytes. */
 #define GMATB_SWS_MMA_CHAIN     0x10000000
+/* gmat_b200 extension bit: keep yuv -> rgb scaling at ratios other than 2:1 on the shared-memory tile kernel
+ * (scale_generic.cuh) instead of the streaming kernel (scale_stream.cuh); same output bytes (A/B measurements, tests). */
+#define GMATB_SWS_TILE_KERNEL   0x08000000
 
 /* ---- interpolation / border codes of the filter layer (NVCV numbering:
  *      NVCV_INTERP_* / NVCV_BORDER_* as used by vf_rotate_nvcv.c:115-135 and
