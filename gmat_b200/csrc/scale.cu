@@ -274,7 +274,7 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
 int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 // any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
-int stream_launch(bool semi, int dc, int nout, dim3 g, cudaStream_t st, const StreamParams &P);
+int stream_launch(bool semi, int dc, int nout, int deal, dim3 g, cudaStream_t st, const StreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -434,7 +434,10 @@ static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst,
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
     dim3 g(c->splan_n, nb, batch);
-    int rc = stream_launch(semi, dc, c->splan_nout, g, c->stream, P);
+    // paired deal of the outputs when two outputs advance ~3 source columns (ratios 1.25 .. 1.75): see the kernel
+    const double r = (double)c->srcW / c->dstW;
+    const int deal = (c->splan_nout == 5 && r >= 1.25 && r <= 1.75) ? 1 : 0;
+    int rc = stream_launch(semi, dc, c->splan_nout, deal, g, c->stream, P);
     *done = (rc == 0);
     return rc;
 }

@@ -42,7 +42,7 @@ static __device__ __noinline__ void stream_store_px3(uint8_t *pp, uint32_t pw) {
     pp[0] = (uint8_t)pw; pp[1] = (uint8_t)(pw >> 8); pp[2] = (uint8_t)(pw >> 16);
 }
 
-template <int L, int DST, int NOUT, int MINB>
+template <int L, int DST, int NOUT, int DEAL, int MINB>
 __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const __grid_constant__ StreamParams P) {
     typedef Raw3<L, 8> Row;
     constexpr int BPP = dst_bpp(DST);
@@ -55,12 +55,18 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
     const int4 pl = P.plan[blockIdx.x];
     const int X0 = pl.x, xoA = pl.y, nout = pl.z, nconv = pl.w;
 
-    // ---- this lane's outputs: columns xoA + lane + 32 i -------------------------------------------------------
+    // ---- this lane's outputs ---------------------------------------------------------------------------------
+    // DEAL 0: output lane + 32 i (round robin).  DEAL 1 (NOUT = 5): outputs 2 lane, 2 lane + 1 (i = 0, 1), 64 + the same
+    // (i = 2, 3) and 128 + lane (i = 4): at ratios near 1.5 neighbouring lanes' taps are then 3 row-buffer entries apart
+    // -- an odd stride: the 16 lanes of an LDS.64 phase hit 16 different bank pairs -- instead of 1.5 (2-way conflicts,
+    // 36 M of 89 M shared-memory wavefronts under ncu).
+    auto out_index = [&](int i) { return DEAL == 0 ? lane + 32 * i : i < 4 ? 64 * (i >> 1) + 2 * lane + (i & 1) : 128 + lane; };
+    static_assert(DEAL == 0 || NOUT == 5, "the paired deal is laid out for 5 outputs per lane");
     float4 wx[NOUT];
     int off[NOUT];
 #pragma unroll
     for (int i = 0; i < NOUT; i++) {
-        const int xo = xoA + min(lane + 32 * i, nout - 1);
+        const int xo = xoA + min(out_index(i), nout - 1);
         wx[i] = __ldg(P.cx + xo);
         off[i] = __ldg(P.px + xo) - X0 + 2;
     }
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
     auto emit = [&](const float (&r0)[NOUT][3], const float (&r1)[NOUT][3], const float (&r2)[NOUT][3], const float (&r3)[NOUT][3]) {
         const float4 w = wy0;
         uint8_t *prow = pd0 + (size_t)yo * pitch_d;
+        uint32_t pw[NOUT];
 #pragma unroll
         for (int i = 0; i < NOUT; i++) {
             int o[3];
@@ -126,16 +133,32 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
                 const float av = gen_chain(w.x, w.y, w.z, w.w, ah[i], ah[i], ah[i], ah[i]);
                 a = max(trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f)), 0) & wmask;
             }
-            const int oi = lane + 32 * i;                              // index of the pixel among the warp's outputs
-            const uint32_t pw = pack4_u8(SW ? o[2] : o[0], o[1], SW ? o[0] : o[2], a);      // saturating
+            pw[i] = pack4_u8(SW ? o[2] : o[0], o[1], SW ? o[0] : o[2], a);      // saturating
+        }
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) {
+            const int oi = out_index(i);                               // index of the pixel among the warp's outputs
             if (BPP == 4) {
-                if (oi < nout) stg32(prow + (size_t)oi * 4, pw);
+                if (oi < nout) stg32(prow + (size_t)oi * 4, pw[i]);
+            } else if (DEAL == 1 && i < 4) {
+                // lanes 2m, 2m+1 hold pixels 4m .. 4m+3 of the group: the even lane stores words 0 and 1, the odd lane word 2
+                if (i & 1) continue;                                   // handled with i - 1
+                const uint32_t nx = __shfl_down_sync(0xffffffffu, pw[i], 1);
+                const int gb = 64 * (i >> 1) + 2 * (lane & ~1);        // first pixel of the group of four
+                if (gb + 3 < nout) {
+                    uint8_t *pg = prow + (size_t)gb * 3;
+                    stg32(pg + ((lane & 1) ? 8 : 0), (lane & 1) ? prmt(pw[i], pw[i + 1], 0x6542u) : prmt(pw[i], pw[i + 1], 0x4210u));
+                    if (!(lane & 1)) stg32(pg + 4, prmt(pw[i + 1], nx, 0x5421u));
+                } else {                                               // ragged last group of the frame's last warp
+                    if (oi < nout) stream_store_px3(prow + (size_t)oi * 3, pw[i]);
+                    if (oi + 1 < nout) stream_store_px3(prow + (size_t)(oi + 1) * 3, pw[i + 1]);
+                }
             } else {
-                const uint32_t nx = __shfl_down_sync(0xffffffffu, pw, 1);
+                const uint32_t nx = __shfl_down_sync(0xffffffffu, pw[i], 1);
                 const int qb = oi & ~3;                                // first pixel of the quad
                 if (qb + 3 < nout) {
-                    if (q < 3) stg32(prow + (size_t)qb * 3 + 4 * q, prmt(pw, nx, selq));
-                } else if (oi < nout) stream_store_px3(prow + (size_t)oi * 3, pw);      // ragged last quad of the frame's last warp
+                    if (q < 3) stg32(prow + (size_t)qb * 3 + 4 * q, prmt(pw[i], nx, selq));
+                } else if (oi < nout) stream_store_px3(prow + (size_t)oi * 3, pw[i]);      // ragged last quad of the frame's last warp
             }
         }
         ++yo;
