@@ -274,7 +274,7 @@ static int launch_fused_d(int dc, bool taps2, bool wrap, dim3 g, cudaStream_t st
 int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 // any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
-int stream_launch(bool semi, int dc, int nout, int deal, dim3 g, cudaStream_t st, const StreamParams &P);
+int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStream_t st, const StreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -398,12 +398,12 @@ static bool build_stream_plan(GmatbSws *c) {
     return true;
 }
 
-// 8-bit yuv 4:2:0 -> 8-bit packed rgb at any ratio, R-B arithmetic: the streaming kernel
+// 8-bit yuv 4:2:0 -> 8-bit packed rgb at any ratio, R-B or R-A arithmetic: the streaming kernel
 static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
     *done = false;
     if (c->splan_state < 0) return 0;
     const int dc = rgb_dst_code(dst->format);
-    if (c->ra || fmt_bits(src->format) != 8 || dc < 0 || dc > D_BGRA || !(c->M.m[1] == 0.f && c->M.m[8] == 0.f)) { c->splan_state = -1; return 0; }
+    if (fmt_bits(src->format) != 8 || dc < 0 || dc > D_BGRA || !(c->M.m[1] == 0.f && c->M.m[8] == 0.f)) { c->splan_state = -1; return 0; }
     if (c->splan_state == 0) {
         if (!build_stream_plan(c)) { c->splan_state = -1; return 0; }
         c->splan_state = 1;
@@ -437,7 +437,7 @@ static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst,
     // paired deal of the outputs when two outputs advance ~3 source columns (ratios 1.25 .. 1.75): see the kernel
     const double r = (double)c->srcW / c->dstW;
     const int deal = (c->splan_nout == 5 && r >= 1.25 && r <= 1.75) ? 1 : 0;
-    int rc = stream_launch(semi, dc, c->splan_nout, deal, g, c->stream, P);
+    int rc = stream_launch(semi, dc, c->splan_nout, deal, c->ra ? 1 : 0, g, c->stream, P);
     *done = (rc == 0);
     return rc;
 }

@@ -42,7 +42,7 @@ static __device__ __noinline__ void stream_store_px3(uint8_t *pp, uint32_t pw) {
     pp[0] = (uint8_t)pw; pp[1] = (uint8_t)(pw >> 8); pp[2] = (uint8_t)(pw >> 16);
 }
 
-template <int L, int DST, int NOUT, int DEAL, int MINB>
+template <int L, int DST, int NOUT, int DEAL, int RA, int MINB>
 __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const __grid_constant__ StreamParams P) {
     typedef Raw3<L, 8> Row;
     constexpr int BPP = dst_bpp(DST);
@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
     // alpha of 4-channel outputs: the chain over the constant 255 the reference's CSC writes, p = 1.0 (scale_generic.cuh)
     float ah[NOUT];
 #pragma unroll
-    for (int i = 0; i < NOUT; i++) ah[i] = gen_chain(wx[i].x, wx[i].y, wx[i].z, wx[i].w, 1.0f, 1.0f, 1.0f, 1.0f);
+    for (int i = 0; i < NOUT; i++) {
+        const float one = RA ? 255.0f : 1.0f;
+        ah[i] = gen_chain(wx[i].x, wx[i].y, wx[i].z, wx[i].w, one, one, one, one);
+    }
 
     // horizontal results of the three source rows before the current pair, oldest first.  (They move down by two rows
     // per step with register copies: with compile-time ring slots instead the step exists in four variants and the
@@ -124,14 +127,19 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
             int o[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const float t = gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
+                // R-A weights are (0, 1-f, f, 0): FFMA(0, p, t) = t exactly, so the outer taps are skipped, not changed
+                const float t = RA ? __fmaf_rn(w.z, r2[i][c], __fmul_rn(w.y, r1[i][c]))
+                                   : gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
+                // R-A: rint + saturate: 1.5 * 2^23 + t rounds to nearest even, its low bits are the integer; the pack saturates
+                if (RA) o[c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
                 // fmaxf(NaN, -1) = -1: a NaN (0/0 Lanczos coefficients, scale_generic.cuh) stores 0 like cvt.rzi.u32.f32
-                o[c] = max(trunc_i(fmaxf(__fmul_rn(t, F.factor), -1.0f)), 0) & wmask;    // the pack saturates the rest
+                else o[c] = max(trunc_i(fmaxf(__fmul_rn(t, F.factor), -1.0f)), 0) & wmask;    // the pack saturates the rest
             }
             int a = 255;
             if (BPP == 4) {
                 const float av = gen_chain(w.x, w.y, w.z, w.w, ah[i], ah[i], ah[i], ah[i]);
-                a = max(trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f)), 0) & wmask;
+                if (RA) a = __float_as_int(__fadd_rn(av, 12582912.0f)) - 0x4B400000;
+                else a = max(trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f)), 0) & wmask;
             }
             pw[i] = pack4_u8(SW ? o[2] : o[0], o[1], SW ? o[0] : o[2], a);      // saturating
         }
@@ -209,7 +217,16 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
                 f2 xg = fma2(fy2, bc(F.m3), bc(t1g));
                 const f2 xb = fma2(fy2, bc(F.m6), bc(t1b));
                 xr = add2(xr, bc(t2r)); xg = add2(xg, bc(t2g));
-                S[h][0] = quant_norm2(xr, F.nk); S[h][1] = quant_norm2(xg, F.nk); S[h][2] = quant_norm2(xb, F.nk);
+                if (RA) {            // integer-valued samples, clamped (gen_sample<1> of scale_generic.cuh)
+                    auto qa = [](f2 x) {
+                        float a, b;
+                        upk(add2(add2_rz(x, bc(GMATB_MAGIC)), bc(-GMATB_MAGIC)), a, b);
+                        return pk(fminf(fmaxf(a, 0.f), 255.f), fminf(fmaxf(b, 0.f), 255.f));
+                    };
+                    S[h][0] = qa(xr); S[h][1] = qa(xg); S[h][2] = qa(xb);
+                } else {
+                    S[h][0] = quant_norm2(xr, F.nk); S[h][1] = quant_norm2(xg, F.nk); S[h][2] = quant_norm2(xb, F.nk);
+                }
             }
             if (lane < nconv) {
 #pragma unroll
@@ -233,7 +250,8 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const f2 *t = &buf[c][off[i]];
-                const f2 hh = gen_chain2(wx[i].x, wx[i].y, wx[i].z, wx[i].w, t[0], t[1], t[2], t[3]);
+                const f2 hh = RA ? fma2(bc(wx[i].z), t[2], mul2(bc(wx[i].y), t[1]))
+                                 : gen_chain2(wx[i].x, wx[i].y, wx[i].z, wx[i].w, t[0], t[1], t[2], t[3]);
                 upk(hh, htop[i][c], hbot[i][c]);
             }
         // ---- vertical pass: output rows whose window ends at row 2kp, then at row 2kp+1 ----------------------------
