@@ -78,7 +78,7 @@ struct GmatbSws {
     bool taps2;
     int iw;   // 0, or 1..3: both axes have the dyadic weights of the exact-integer kernel (scale_fused4i.cuh)
     // any-ratio streaming kernel (scale_stream.cuh): which strip / outputs each warp owns; built on first use
-    int4 *splan; int splan_n, splan_nout, splan_state;   // state: 0 not built, 1 ready, -1 does not apply
+    int4 *splan[2]; int splan_n[2], splan_nout[2], splan_state[2];   // per filter bank; state: 0 not built, 1 ready, -1 does not apply
     // scratch
     void *tmp; size_t tmp_size;
     void *stage_src, *stage_dst; size_t stage_src_size, stage_dst_size;
@@ -123,7 +123,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
     c->tmp = c->stage_src = c->stage_dst = nullptr;
     c->tmp_size = c->stage_src_size = c->stage_dst_size = 0;
     c->pipe = nullptr;
-    c->splan = nullptr; c->splan_n = c->splan_nout = c->splan_state = 0;
+    for (int i = 0; i < 2; i++) { c->splan[i] = nullptr; c->splan_n[i] = c->splan_nout[i] = c->splan_state[i] = 0; }
     c->srcW = srcW; c->srcH = srcH; c->srcFmt = srcFormat; c->dstW = dstW; c->dstH = dstH; c->dstFmt = dstFormat;
     c->flags = flags; c->cspace = colorspace; c->stream = 0;
     c->param[0] = param ? param[0] : GMATB_SWS_PARAM_DEFAULT;
@@ -205,7 +205,7 @@ extern "C" void gmatb_sws_free(GmatbSws *c) {
     for (int i = 0; i < 2; i++) {
         cudaFree(c->cx[i]); cudaFree(c->cy[i]); cudaFree(c->px[i]); cudaFree(c->py[i]);
     }
-    cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst); cudaFree(c->splan);
+    cudaFree(c->tmp); cudaFree(c->stage_src); cudaFree(c->stage_dst); cudaFree(c->splan[0]); cudaFree(c->splan[1]);
     host_pipe_free(c->pipe);
     delete c;
 }
@@ -275,6 +275,7 @@ int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t 
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 // any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
 int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStream_t st, const StreamParams &P);
+int plane_stream_launch(int ch, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -366,10 +367,9 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
 // The warps of the streaming kernel: greedy cut of the output columns.  A warp converts source columns [X0, X0 + 8 lanes)
 // (X0 a multiple of 8, at most 256 columns) and owns outputs [xo, xo + n): every tap of every owned output, clamped to the
 // frame, must lie in its strip (taps left of column 0 / right of column W-1 are the replicated pad entries).
-static bool build_stream_plan(GmatbSws *c) {
-    const std::vector<int> &px = c->hpx[0];
-    const int W = c->srcW, dW = c->dstW;
-    if (W < 16 || c->srcH < 2 || dW < 1 || (int)px.size() != dW) return false;
+static bool build_stream_plan(GmatbSws *c, int bank, int W, int srcH, int dW) {
+    const std::vector<int> &px = c->hpx[bank];
+    if (W < 16 || srcH < 2 || dW < 1 || (int)px.size() != dW) return false;
     const double r = (double)W / dW;
     if (r > 48.0) return false;
     const int nout = r >= 2.5 ? 3 : 5;
@@ -392,21 +392,21 @@ static bool build_stream_plan(GmatbSws *c) {
         plan.push_back(make_int4(X0, xo, n, (last - X0) / 8 + 1));
         xo += n;
     }
-    if (cudaMalloc(&c->splan, plan.size() * sizeof(int4)) != cudaSuccess) return false;
-    if (cudaMemcpy(c->splan, plan.data(), plan.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    c->splan_n = (int)plan.size(); c->splan_nout = nout;
+    if (cudaMalloc(&c->splan[bank], plan.size() * sizeof(int4)) != cudaSuccess) return false;
+    if (cudaMemcpy(c->splan[bank], plan.data(), plan.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    c->splan_n[bank] = (int)plan.size(); c->splan_nout[bank] = nout;
     return true;
 }
 
 // 8-bit yuv 4:2:0 -> 8-bit packed rgb at any ratio, R-B or R-A arithmetic: the streaming kernel
 static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, bool *done) {
     *done = false;
-    if (c->splan_state < 0) return 0;
+    if (c->splan_state[0] < 0) return 0;
     const int dc = rgb_dst_code(dst->format);
-    if (fmt_bits(src->format) != 8 || dc < 0 || dc > D_BGRA || !(c->M.m[1] == 0.f && c->M.m[8] == 0.f)) { c->splan_state = -1; return 0; }
-    if (c->splan_state == 0) {
-        if (!build_stream_plan(c)) { c->splan_state = -1; return 0; }
-        c->splan_state = 1;
+    if (fmt_bits(src->format) != 8 || dc < 0 || dc > D_BGRA || !(c->M.m[1] == 0.f && c->M.m[8] == 0.f)) { c->splan_state[0] = -1; return 0; }
+    if (c->splan_state[0] == 0) {
+        if (!build_stream_plan(c, 0, c->srcW, c->srcH, c->dstW)) { c->splan_state[0] = -1; return 0; }
+        c->splan_state[0] = 1;
     }
     StreamParams P;
     memset(&P, 0, sizeof(P));
@@ -424,20 +424,20 @@ static int run_stream(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst,
     P.F.factor = 255.f;
     P.F.dstW = c->dstW; P.F.dstH = c->dstH;
     P.cx = c->cx[0]; P.cy = c->cy[0]; P.px = c->px[0]; P.py = c->py[0];
-    P.plan = c->splan;
+    P.plan = c->splan[0];
     P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
     const int batch = src->batch > 1 ? src->batch : 1;
     // bands: enough warps for a few waves of 148 SMs x 12-16 resident warps, no shorter than 16 output rows
     long long want = 148LL * 16 * 6;
-    int nb = (int)((want + (long long)c->splan_n * batch - 1) / ((long long)c->splan_n * batch));
+    int nb = (int)((want + (long long)c->splan_n[0] * batch - 1) / ((long long)c->splan_n[0] * batch));
     nb = std::max(1, std::min(nb, (c->dstH + 15) / 16));
     P.band = (c->dstH + nb - 1) / nb;
     nb = (c->dstH + P.band - 1) / P.band;
-    dim3 g(c->splan_n, nb, batch);
+    dim3 g(c->splan_n[0], nb, batch);
     // paired deal of the outputs when two outputs advance ~3 source columns (ratios 1.25 .. 1.75): see the kernel
     const double r = (double)c->srcW / c->dstW;
-    const int deal = (c->splan_nout == 5 && r >= 1.25 && r <= 1.75) ? 1 : 0;
-    int rc = stream_launch(semi, dc, c->splan_nout, deal, c->ra ? 1 : 0, g, c->stream, P);
+    const int deal = (c->splan_nout[0] == 5 && r >= 1.25 && r <= 1.75) ? 1 : 0;
+    int rc = stream_launch(semi, dc, c->splan_nout[0], deal, c->ra ? 1 : 0, g, c->stream, P);
     *done = (rc == 0);
     return rc;
 }
@@ -551,6 +551,28 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     si.pl[0].p = (uint8_t *)s->data[plane]; si.pl[0].pitch = s->linesize[plane]; si.pl[0].bstride = s->batch > 1 ? s->batch_stride[plane] : 0;
     di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
+    // 8-bit planes of 1 or 2 components: the streaming kernel (scale_stream.cuh)
+    if (bits == 8 && (ch == 1 || ch == 2) && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->splan_state[bank] >= 0 &&
+        planes_aligned(si, 1, 8 * ch) && planes_aligned(di, 1, 4) && si.pl[0].pitch >= ((pw + 7) & ~7) * ch) {
+        if (c->splan_state[bank] == 0) c->splan_state[bank] = build_stream_plan(c, bank, pw, ph, dw) ? 1 : -1;
+        if (c->splan_state[bank] == 1) {
+            PlaneStreamParams P;
+            memset(&P, 0, sizeof(P));
+            P.src = si.pl[0]; P.dst = di.pl[0];
+            P.W = pw; P.H = ph; P.dstW = dw; P.dstH = dh;
+            P.nk = norm_k(8);
+            P.cx = c->cx[bank]; P.cy = c->cy[bank]; P.px = c->px[bank]; P.py = c->py[bank];
+            P.plan = c->splan[bank];
+            P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
+            const int batch = s->batch > 1 ? s->batch : 1;
+            long long want = 148LL * 16 * 6;
+            int nb = (int)((want + (long long)c->splan_n[bank] * batch - 1) / ((long long)c->splan_n[bank] * batch));
+            nb = std::max(1, std::min(nb, (dh + 15) / 16));
+            P.band = (dh + nb - 1) / nb;
+            nb = (dh + P.band - 1) / P.band;
+            return plane_stream_launch(ch, c->splan_nout[bank], c->ra ? 1 : 0, dim3(c->splan_n[bank], nb, batch), c->stream, P);
+        }
+    }
     return run_generic(c, bank, si, di, dw, dh, GS_PACKED, ch, bits, 0, s->batch);
 }
 

@@ -274,4 +274,194 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same machine for ONE PLANE of 8-bit samples with CH = 1 or 2 interleaved components (the Y and UV planes of
+// nv12 / yuv420p -> same format scaling: what the scale_cuda filter and the yuv -> yuv branch of sws_scale do,
+// swscale_cuda.c:372-476; any ratio, 2:1 included).  No colour conversion: a sample is RN(j / 255) (R-B) or j (R-A).
+// A lane owns 8 pixels of both rows of a pair; outputs leave through a small shared-memory row so that the warp
+// stores whole words.
+struct PlaneStreamParams {
+    Plane src, dst;
+    int W, H, dstW, dstH;
+    NormK nk;
+    const float4 *cx, *cy;
+    const int *px, *py;
+    const int4 *plan;
+    int band, wrap;
+};
+
+template <int CH, int NOUT, int RA, int MINB>
+__global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __grid_constant__ PlaneStreamParams P) {
+    __shared__ __align__(16) f2 buf[CH][GMATB_STREAM_BUF];
+    __shared__ __align__(16) uint8_t orow[32 * NOUT * CH];
+    const int lane = threadIdx.x;
+    const long long fz = blockIdx.z;
+    const int W = P.W, H = P.H;
+    const int4 pl = P.plan[blockIdx.x];
+    const int X0 = pl.x, xoA = pl.y, nout = pl.z, nconv = pl.w;
+    float4 wx[NOUT];
+    int off[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; i++) {
+        const int xo = xoA + min(lane + 32 * i, nout - 1);
+        wx[i] = __ldg(P.cx + xo);
+        off[i] = __ldg(P.px + xo) - X0 + 2;
+    }
+    const int yo_begin = blockIdx.y * P.band, yo_end = min(yo_begin + P.band, P.dstH);
+    const int v_first = __ldg(P.py + yo_begin), v_last = __ldg(P.py + yo_end - 1) + 3;
+    const int kp_start = v_first >> 1, kp_last = v_last >> 1;
+
+    const int cs = min(X0 + 8 * lane, (W - 1) & ~7);
+    const uint8_t *ps = P.src.p + fz * P.src.bstride + (size_t)cs * CH;
+    const unsigned pitch_s = P.src.pitch, pitch_d = P.dst.pitch;
+    struct Rows { uint32_t t[2 * CH], b[2 * CH]; };
+    auto load_pair = [&](int kp, Rows &R) {
+        const unsigned rt = (unsigned)min(max(2 * kp, 0), H - 1), rb = (unsigned)min(max(2 * kp + 1, 0), H - 1);
+        if (CH == 1) {
+            const uint2 a = ldg64(ps + rt * pitch_s), b = ldg64(ps + rb * pitch_s);
+            R.t[0] = a.x; R.t[1] = a.y; R.b[0] = b.x; R.b[1] = b.y;
+        } else {
+            const uint4 a = ldg128(ps + rt * pitch_s), b = ldg128(ps + rb * pitch_s);
+            R.t[0] = a.x; R.t[1] = a.y; R.t[2 * CH - 2] = a.z; R.t[2 * CH - 1] = a.w;
+            R.b[0] = b.x; R.b[1] = b.y; R.b[2 * CH - 2] = b.z; R.b[2 * CH - 1] = b.w;
+        }
+    };
+    uint8_t *pd0 = P.dst.p + fz * P.dst.bstride + (size_t)xoA * CH;
+    const int wmask = P.wrap ? 0xFF : 0x7fffffff;
+    const float factor = 255.0f;
+
+    float hist[3][NOUT][CH];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int i = 0; i < NOUT; i++)
+#pragma unroll
+            for (int c = 0; c < CH; c++) hist[s][i][c] = 0.f;
+    int yo = yo_begin;
+    int pend0 = v_first + 3, pend1 = yo + 1 < yo_end ? __ldg(P.py + yo + 1) + 3 : 0x7fffffff;
+    float4 wy0 = __ldg(P.cy + yo), wy1 = __ldg(P.cy + min(yo + 1, yo_end - 1));
+
+    auto emit = [&](const float (&r0)[NOUT][CH], const float (&r1)[NOUT][CH], const float (&r2)[NOUT][CH], const float (&r3)[NOUT][CH]) {
+        const float4 w = wy0;
+        __syncwarp();                                  // the previous row's copy-out has read the staging row
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) {
+            int o[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const float t = RA ? __fmaf_rn(w.z, r2[i][c], __fmul_rn(w.y, r1[i][c]))
+                                   : gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
+                if (RA) o[c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
+                else o[c] = max(trunc_i(fmaxf(__fmul_rn(t, factor), -1.0f)), 0) & wmask;
+            }
+            const uint32_t pw = pack4_u8(o[0], CH > 1 ? o[CH - 1] : 0, 0, 0);      // saturating
+            if (CH == 1) orow[lane + 32 * i] = (uint8_t)pw;
+            else reinterpret_cast<unsigned short *>(orow)[lane + 32 * i] = (unsigned short)pw;
+        }
+        __syncwarp();
+        uint8_t *prow = pd0 + (size_t)yo * pitch_d;
+        const int nbytes = nout * CH;
+#pragma unroll
+        for (int t = 0; t < (NOUT * CH + 3) / 4; t++) {
+            const int wd = lane + 32 * t;
+            if (4 * wd + 3 < nbytes) stg32(prow + 4 * wd, reinterpret_cast<const uint32_t *>(orow)[wd]);
+            else {
+#pragma unroll 1
+                for (int b = 4 * wd; b < nbytes; b++) prow[b] = orow[b];
+            }
+        }
+        ++yo;
+        pend0 = pend1; wy0 = wy1;
+        if (yo + 1 < yo_end) { pend1 = __ldg(P.py + yo + 1) + 3; wy1 = __ldg(P.cy + yo + 1); }
+        else pend1 = 0x7fffffff;
+    };
+
+    // bank-conflict-free publication: as in the yuv kernel, lane l walks its 4 column pairs in the order j + rot
+    const int rot = (lane >> 1) & 3;
+    f2 *wpos[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) wpos[j] = &buf[0][8 * lane + 2 + 2 * ((j + rot) & 3)];
+    const bool lpad = X0 == 0, rpad = X0 + 8 * nconv >= W;
+
+    auto sample2 = [&](float mt, float mb) -> f2 {     // (top, bottom) magic floats -> samples
+        if (RA) return add2(pk(mt, mb), bc(-GMATB_MAGIC));
+        return norm2_inrange(mt, mb, P.nk);
+    };
+    auto step = [&](const Rows &now, int kp) {
+        // bytes of this lane's 8 pixels, rotated by 2 rot pixels
+        uint32_t wt[2 * CH], wb[2 * CH];
+#pragma unroll
+        for (int k = 0; k < 2 * CH; k++) { wt[k] = now.t[k]; wb[k] = now.b[k]; }
+        if (CH == 1) {
+            const int bits = 16 * rot;
+            const uint32_t tl = (bits & 32) ? wt[1] : wt[0], th = (bits & 32) ? wt[0] : wt[1];
+            const uint32_t bl = (bits & 32) ? wb[1] : wb[0], bh = (bits & 32) ? wb[0] : wb[1];
+            wt[0] = __funnelshift_r(tl, th, bits & 31); wt[1] = __funnelshift_r(th, tl, bits & 31);
+            wb[0] = __funnelshift_r(bl, bh, bits & 31); wb[1] = __funnelshift_r(bh, bl, bits & 31);
+        } else {                                       // 4 words of 2 pixels each: rotate whole words
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { a[k] = wt[k]; b[k] = wb[k]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                wt[k] = rot == 0 ? a[k] : rot == 1 ? a[(k + 1) & 3] : rot == 2 ? a[(k + 2) & 3] : a[(k + 3) & 3];
+                wb[k] = rot == 0 ? b[k] : rot == 1 ? b[(k + 1) & 3] : rot == 2 ? b[(k + 2) & 3] : b[(k + 3) & 3];
+            }
+        }
+        __syncwarp();                                  // the previous step's taps have been read
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                  // pixels 2j, 2j+1 (after rotation)
+            f2 S[2][CH];
+            if (CH == 1) {
+                const uint32_t a = wt[j >> 1], b = wb[j >> 1];
+                if (j & 1) { S[0][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][0] = sample2(byte_magic<3>(a), byte_magic<3>(b)); }
+                else       { S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[1][0] = sample2(byte_magic<1>(a), byte_magic<1>(b)); }
+            } else {
+                const uint32_t a = wt[j], b = wb[j];
+                S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[0][CH - 1] = sample2(byte_magic<1>(a), byte_magic<1>(b));
+                S[1][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][CH - 1] = sample2(byte_magic<3>(a), byte_magic<3>(b));
+            }
+            if (lane < nconv) {
+#pragma unroll
+                for (int c = 0; c < CH; c++)
+                    *reinterpret_cast<ulonglong2 *>(wpos[j] + c * GMATB_STREAM_BUF) = make_ulonglong2(S[0][c], S[1][c]);
+                if (lpad && lane == 0 && j == 0) {
+#pragma unroll
+                    for (int c = 0; c < CH; c++) *reinterpret_cast<ulonglong2 *>(&buf[c][0]) = make_ulonglong2(S[0][c], S[0][c]);
+                }
+            }
+        }
+        __syncwarp();
+        if (rpad) {
+            if (lane < CH) { const f2 e = buf[lane][W - 1 - X0 + 2]; buf[lane][W - X0 + 2] = e; buf[lane][W - X0 + 3] = e; }
+            __syncwarp();
+        }
+        float htop[NOUT][CH], hbot[NOUT][CH];
+#pragma unroll
+        for (int i = 0; i < NOUT; i++)
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const f2 *t = &buf[c][off[i]];
+                const f2 hh = RA ? fma2(bc(wx[i].z), t[2], mul2(bc(wx[i].y), t[1]))
+                                 : gen_chain2(wx[i].x, wx[i].y, wx[i].z, wx[i].w, t[0], t[1], t[2], t[3]);
+                upk(hh, htop[i][c], hbot[i][c]);
+            }
+        while (pend0 == 2 * kp) emit(hist[0], hist[1], hist[2], htop);
+        while (pend0 == 2 * kp + 1) emit(hist[1], hist[2], htop, hbot);
+#pragma unroll
+        for (int i = 0; i < NOUT; i++)
+#pragma unroll
+            for (int c = 0; c < CH; c++) { hist[0][i][c] = hist[2][i][c]; hist[1][i][c] = htop[i][c]; hist[2][i][c] = hbot[i][c]; }
+    };
+
+    Rows cur, nxt;
+    load_pair(kp_start, cur);
+#pragma unroll 1
+    for (int kp = kp_start; kp <= kp_last; kp++) {
+        if (kp < kp_last) load_pair(kp + 1, nxt);
+        step(cur, kp);
+        cur = nxt;
+    }
+}
+
 }  // namespace gmatb

@@ -55,3 +55,16 @@ def test_stream_full_sizes(dev, sw, sh, dw, dh):
         _, _, a = run(dev, FMT.NV12, FMT.RGB24, sw, sh, dw, dh, flag, param, seed=7)
         _, _, b = run(dev, FMT.NV12, FMT.RGB24, sw, sh, dw, dh, flag, param, extra=SWS.TILE_KERNEL, seed=7)
         assert torch.equal(a.buf, b.buf), f"{(a.buf != b.buf).sum().item()} bytes differ"
+
+
+# ---- yuv -> yuv: every plane through the plane form of the streaming kernel (what the scale_cuda filter runs) -----------
+@pytest.mark.parametrize("name,flag,param", ALGOS)
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (3840, 2160, 1920, 1080), (640, 360, 1280, 720), (64, 48, 40, 30), (66, 34, 100, 58),
+                                         (32, 32, 14, 10), (200, 120, 24, 14), (500, 68, 2000, 70), (2000, 72, 500, 144), (1054, 126, 666, 80),
+                                         (3840, 32, 1280, 12), (1440, 100, 48, 100), (48, 100, 1440, 100), (36, 4, 14, 6)])
+def test_plane_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):
+    for fmt, wrap in ((FMT.NV12, 0), (FMT.YUV420P, SWS.PARITY_WRAP)):
+        _, _, a = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, seed=sw + dh)
+        _, _, b = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
+        if not torch.equal(a.buf, b.buf):
+            assert_same(a, b, f"plane stream vs tile kernel {name}{param} {fmt} {sw}x{sh}->{dw}x{dh}")
