@@ -458,6 +458,19 @@ def main():
                                ("C2 frames, tensor-pipe form of the headline kernel (SWS.MMA_CHAIN: horizontal pass on IMMA u8 x s8, same bytes)", SWS.BICUBIC | SWS.MMA_CHAIN, (0.75,))):
             c2 = SwsContext(sw, sh, sfmt, dw, dh, dfmt, fl | SWS.HWACCEL_CUDA, par)
             sec(label, lambda c2=c2: c2.scale(src, dst), px, alg_bytes_launch)
+        # other ratios than 2:1 (the any-ratio streaming kernel, scale_stream.cuh), 32 frames per GPU
+        for label, (aw, ah, bw, bh), afmt, bfmt, fl, par, obpp in (
+                ("1080p NV12 -> 720p RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (1920, 1080, 1280, 720), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
+                ("4K NV12 -> 720p RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (3840, 2160, 1280, 720), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
+                ("1080p NV12 -> 4K RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (1920, 1080, 3840, 2160), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
+                ("4K NV12 -> 1080p NV12, bicubic R-B default parameter (plane streaming kernel: the scale_cuda filter's path)", (3840, 2160, 1920, 1080), FMT.NV12, FMT.NV12, SWS.BICUBIC, None, 1.5)):
+            nb_ = 16 if bw > aw else 32
+            sa = FrameBatch(afmt, aw, ah, nb_, device=dev); sa.buf.random_(0, 256)
+            sb = FrameBatch(bfmt, bw, bh, nb_, device=dev)
+            cs_ = SwsContext(aw, ah, afmt, bw, bh, bfmt, fl | SWS.HWACCEL_CUDA, par)
+            sec(label, lambda cs_=cs_, sa=sa, sb=sb: cs_.scale(sa, sb), nb_ * aw * ah, nb_ * (aw * ah * 1.5 + bw * bh * obpp), steps=5)
+            del sa, sb, cs_
+        torch.cuda.empty_cache()
         f4, p4, a4, d4 = c4_workload(dev, max(1, 256 // max(world, 8)))      # BASELINE configs[3]: batch 256 over 8 GPUs
         sec(d4, f4, p4, a4, steps=5)
         del f4

@@ -177,14 +177,17 @@ __global__ void __launch_bounds__(256) rotate_linear_tma_kernel(const __grid_con
                                                                 int box_x, int box_y) {
     extern __shared__ __align__(128) uint8_t rot_tile[];
     __shared__ uint64_t bar;
+    __shared__ int tile_info[4];                                  // interior?, bx0, by0 and the corner minima as float bits
+    __shared__ float tile_min[2];
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
     const int x0 = tx0 + threadIdx.x * 4, y = ty0 + threadIdx.y;
     const long long fz = blockIdx.z;
     const int W = s.w, H = s.h;
-    // the four corners of the tile (clipped to the destination), through the per-pixel formula
-    const int tx1 = min(tx0 + 31, d.w - 1), ty1 = min(ty0 + 31, d.h - 1);
-    float cminx, cmaxx, cminy, cmaxy;
-    {
+    // ONE thread maps the four corners of the tile (clipped to the destination) through the per-pixel formula, decides
+    // whether the footprint lies inside the source and, if so, starts the TMA load (as 256 per-thread copies this
+    // prologue was ~19 of the kernel's 117 instructions per pixel)
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int tx1 = min(tx0 + 31, d.w - 1), ty1 = min(ty0 + 31, d.h - 1);
         float cx[4], cy[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -192,24 +195,29 @@ __global__ void __launch_bounds__(256) rotate_linear_tma_kernel(const __grid_con
             cx[k] = (float)__dsub_rn(__dmul_rn(dxk, R.c), __dmul_rn(dyk, R.s));
             cy[k] = (float)__dadd_rn(__dmul_rn(dxk, R.s), __dmul_rn(dyk, R.c));
         }
-        cminx = fminf(fminf(cx[0], cx[1]), fminf(cx[2], cx[3])); cmaxx = fmaxf(fmaxf(cx[0], cx[1]), fmaxf(cx[2], cx[3]));
-        cminy = fminf(fminf(cy[0], cy[1]), fminf(cy[2], cy[3])); cmaxy = fmaxf(fmaxf(cy[0], cy[1]), fmaxf(cy[2], cy[3]));
+        const float cminx = fminf(fminf(cx[0], cx[1]), fminf(cx[2], cx[3])), cmaxx = fmaxf(fmaxf(cx[0], cx[1]), fmaxf(cx[2], cx[3]));
+        const float cminy = fminf(fminf(cy[0], cy[1]), fminf(cy[2], cy[3])), cmaxy = fmaxf(fmaxf(cy[0], cy[1]), fmaxf(cy[2], cy[3]));
+        const int bx0_ = (int)cminx, by0_ = (int)cminy;             // used only when both are >= 0
+        // the tile's first byte: TMA wants the innermost coordinate of a byte tensor on a 16-byte boundary (an unaligned one
+        // raises an illegal-instruction error on B200: tools/tma_probe2.cu)
+        const int xb_ = (bx0_ * BPP) & ~15;
+        const bool in = cminx >= 0.0f && cminy >= 0.0f && cmaxx < (float)(W - 1) && cmaxy < (float)(H - 1) &&
+                        ((int)cmaxx + 2) * BPP + 8 - xb_ <= box_x && (int)cmaxy + 2 - by0_ <= box_y;
+        tile_info[0] = in; tile_info[1] = xb_; tile_info[2] = by0_;
+        tile_min[0] = cminx; tile_min[1] = cminy;
+        if (in) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)(box_x * box_y));
+            tma_load_3d(rot_tile, &smap, &bar, xb_, by0_, (int)fz);
+        }
     }
-    const int bx0 = (int)cminx, by0 = (int)cminy;                 // used only when both are >= 0
-    // the tile's first byte: TMA wants the innermost coordinate of a byte tensor on a 16-byte boundary (an unaligned one
-    // raises an illegal-instruction error on B200: tools/tma_probe2.cu)
-    const int xb = (bx0 * BPP) & ~15;
-    const bool interior = cminx >= 0.0f && cminy >= 0.0f && cmaxx < (float)(W - 1) && cmaxy < (float)(H - 1) &&
-                          ((int)cmaxx + 2) * BPP + 8 - xb <= box_x && (int)cmaxy + 2 - by0 <= box_y;
+    __syncthreads();
+    const bool interior = tile_info[0] != 0;
+    const int xb = tile_info[1], by0 = tile_info[2];
+    const float cminx = tile_min[0], cminy = tile_min[1];
     if (!interior) {                                              // block-uniform
         if (x0 < d.w && y < d.h) rotate4_global<BPP>(s, d, R, x0, y, fz);
         return;
-    }
-    if (threadIdx.x == 0 && threadIdx.y == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        mbar_expect_tx(&bar, (uint32_t)(box_x * box_y));
-        tma_load_3d(rot_tile, &smap, &bar, xb, by0, (int)fz);
     }
     const bool active = x0 < d.w && y < d.h;
     // coordinates while the tile is in flight

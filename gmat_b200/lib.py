@@ -40,8 +40,7 @@ _lib = None
 
 
 def lib_path():
-    # GMATB_LIB: an alternative build of the same library (kernel tuning experiments, tools/)
-    return os.environ.get("GMATB_LIB") or os.path.join(_HERE, "libgmat_b200.so")
+    return os.path.join(_HERE, "libgmat_b200.so")
 
 
 def lib():
