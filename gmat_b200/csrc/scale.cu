@@ -275,7 +275,7 @@ int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t 
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 // any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
 int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStream_t st, const StreamParams &P);
-int plane_stream_launch(int ch, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P);
+int plane_stream_launch(int ch, int bits, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -551,16 +551,17 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     si.pl[0].p = (uint8_t *)s->data[plane]; si.pl[0].pitch = s->linesize[plane]; si.pl[0].bstride = s->batch > 1 ? s->batch_stride[plane] : 0;
     di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
-    // 8-bit planes of 1 or 2 components: the streaming kernel (scale_stream.cuh)
-    if (bits == 8 && (ch == 1 || ch == 2) && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->splan_state[bank] >= 0 &&
-        planes_aligned(si, 1, 8 * ch) && planes_aligned(di, 1, 4) && si.pl[0].pitch >= ((pw + 7) & ~7) * ch) {
+    // 8- and 16-bit planes of 1 or 2 components: the streaming kernel (scale_stream.cuh)
+    const int bp = ch * bits / 8;
+    if ((ch == 1 || ch == 2) && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->splan_state[bank] >= 0 &&
+        planes_aligned(si, 1, bp == 1 ? 8 : 16) && planes_aligned(di, 1, 4) && si.pl[0].pitch >= ((pw + 7) & ~7) * bp) {
         if (c->splan_state[bank] == 0) c->splan_state[bank] = build_stream_plan(c, bank, pw, ph, dw) ? 1 : -1;
         if (c->splan_state[bank] == 1) {
             PlaneStreamParams P;
             memset(&P, 0, sizeof(P));
             P.src = si.pl[0]; P.dst = di.pl[0];
             P.W = pw; P.H = ph; P.dstW = dw; P.dstH = dh;
-            P.nk = norm_k(8);
+            P.nk = norm_k(bits);
             P.cx = c->cx[bank]; P.cy = c->cy[bank]; P.px = c->px[bank]; P.py = c->py[bank];
             P.plan = c->splan[bank];
             P.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
@@ -570,7 +571,7 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
             nb = std::max(1, std::min(nb, (dh + 15) / 16));
             P.band = (dh + nb - 1) / nb;
             nb = (dh + P.band - 1) / P.band;
-            return plane_stream_launch(ch, c->splan_nout[bank], c->ra ? 1 : 0, dim3(c->splan_n[bank], nb, batch), c->stream, P);
+            return plane_stream_launch(ch, bits, c->splan_nout[bank], c->ra ? 1 : 0, dim3(c->splan_n[bank], nb, batch), c->stream, P);
         }
     }
     return run_generic(c, bank, si, di, dw, dh, GS_PACKED, ch, bits, 0, s->batch);

@@ -36,13 +36,14 @@ int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStr
     return semi ? launch_stream_d<L_NV12>(dc, nout, deal, ra, g, st, P) : launch_stream_d<L_I420>(dc, nout, deal, ra, g, st, P);
 }
 
-template <int CH>
+template <int CH, int SBITS>
 static void launch_plane_t(int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P) {
-    if (ra) { if (nout <= 3) plane_scale_stream_kernel<CH, 3, 1, 16><<<g, 32, 0, st>>>(P); else plane_scale_stream_kernel<CH, 5, 1, 16><<<g, 32, 0, st>>>(P); }
-    else    { if (nout <= 3) plane_scale_stream_kernel<CH, 3, 0, 16><<<g, 32, 0, st>>>(P); else plane_scale_stream_kernel<CH, 5, 0, 16><<<g, 32, 0, st>>>(P); }
+    if (ra) { if (nout <= 3) plane_scale_stream_kernel<CH, SBITS, 3, 1, 16><<<g, 32, 0, st>>>(P); else plane_scale_stream_kernel<CH, SBITS, 5, 1, 16><<<g, 32, 0, st>>>(P); }
+    else    { if (nout <= 3) plane_scale_stream_kernel<CH, SBITS, 3, 0, 16><<<g, 32, 0, st>>>(P); else plane_scale_stream_kernel<CH, SBITS, 5, 0, 16><<<g, 32, 0, st>>>(P); }
 }
-int plane_stream_launch(int ch, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P) {
-    if (ch == 1) launch_plane_t<1>(nout, ra, g, st, P); else launch_plane_t<2>(nout, ra, g, st, P);
+int plane_stream_launch(int ch, int bits, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P) {
+    if (bits == 8) { if (ch == 1) launch_plane_t<1, 8>(nout, ra, g, st, P); else launch_plane_t<2, 8>(nout, ra, g, st, P); }
+    else           { if (ch == 1) launch_plane_t<1, 16>(nout, ra, g, st, P); else launch_plane_t<2, 16>(nout, ra, g, st, P); }
     count_launch();
     return set_cuda_error(cudaGetLastError());
 }

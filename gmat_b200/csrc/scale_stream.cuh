@@ -275,9 +275,9 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The same machine for ONE PLANE of 8-bit samples with CH = 1 or 2 interleaved components (the Y and UV planes of
-// nv12 / yuv420p -> same format scaling: what the scale_cuda filter and the yuv -> yuv branch of sws_scale do,
-// swscale_cuda.c:372-476; any ratio, 2:1 included).  No colour conversion: a sample is RN(j / 255) (R-B) or j (R-A).
+// The same machine for ONE PLANE of 8- or 16-bit samples with CH = 1 or 2 interleaved components (the Y and UV planes of
+// nv12 / yuv420p / p010 / p016 -> same format scaling: what the scale_cuda filter and the yuv -> yuv branch of sws_scale
+// do, swscale_cuda.c:372-476; any ratio, 2:1 included).  No colour conversion: a sample is RN(j / max) (R-B) or j (R-A).
 // A lane owns 8 pixels of both rows of a pair; outputs leave through a small shared-memory row so that the warp
 // stores whole words.
 struct PlaneStreamParams {
@@ -290,10 +290,13 @@ struct PlaneStreamParams {
     int band, wrap;
 };
 
-template <int CH, int NOUT, int RA, int MINB>
+template <int CH, int SBITS, int NOUT, int RA, int MINB>
 __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __grid_constant__ PlaneStreamParams P) {
+    constexpr int BP = CH * SBITS / 8;                // bytes per pixel: 1, 2, 2, 4
+    constexpr int NW = 2 * BP;                        // words of a lane's 8 pixels
+    constexpr int SMAX = SBITS == 8 ? 255 : 65535;
     __shared__ __align__(16) f2 buf[CH][GMATB_STREAM_BUF];
-    __shared__ __align__(16) uint8_t orow[32 * NOUT * CH];
+    __shared__ __align__(16) uint8_t orow[32 * NOUT * BP];
     const int lane = threadIdx.x;
     const long long fz = blockIdx.z;
     const int W = P.W, H = P.H;
@@ -312,23 +315,26 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
     const int kp_start = v_first >> 1, kp_last = v_last >> 1;
 
     const int cs = min(X0 + 8 * lane, (W - 1) & ~7);
-    const uint8_t *ps = P.src.p + fz * P.src.bstride + (size_t)cs * CH;
+    const uint8_t *ps = P.src.p + fz * P.src.bstride + (size_t)cs * BP;
     const unsigned pitch_s = P.src.pitch, pitch_d = P.dst.pitch;
-    struct Rows { uint32_t t[2 * CH], b[2 * CH]; };
-    auto load_pair = [&](int kp, Rows &R) {
-        const unsigned rt = (unsigned)min(max(2 * kp, 0), H - 1), rb = (unsigned)min(max(2 * kp + 1, 0), H - 1);
-        if (CH == 1) {
-            const uint2 a = ldg64(ps + rt * pitch_s), b = ldg64(ps + rb * pitch_s);
-            R.t[0] = a.x; R.t[1] = a.y; R.b[0] = b.x; R.b[1] = b.y;
-        } else {
-            const uint4 a = ldg128(ps + rt * pitch_s), b = ldg128(ps + rb * pitch_s);
-            R.t[0] = a.x; R.t[1] = a.y; R.t[2 * CH - 2] = a.z; R.t[2 * CH - 1] = a.w;
-            R.b[0] = b.x; R.b[1] = b.y; R.b[2 * CH - 2] = b.z; R.b[2 * CH - 1] = b.w;
+    struct Rows { uint32_t t[NW], b[NW]; };
+    auto load_row = [&](const uint8_t *q, uint32_t (&w)[NW]) {
+        if (NW == 2) { const uint2 a = ldg64(q); w[0] = a.x; w[1] = a.y; }
+        else {
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 a = ldg128(q + 16 * k);
+                w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
+            }
         }
     };
-    uint8_t *pd0 = P.dst.p + fz * P.dst.bstride + (size_t)xoA * CH;
-    const int wmask = P.wrap ? 0xFF : 0x7fffffff;
-    const float factor = 255.0f;
+    auto load_pair = [&](int kp, Rows &R) {
+        const unsigned rt = (unsigned)min(max(2 * kp, 0), H - 1), rb = (unsigned)min(max(2 * kp + 1, 0), H - 1);
+        load_row(ps + rt * pitch_s, R.t); load_row(ps + rb * pitch_s, R.b);
+    };
+    uint8_t *pd0 = P.dst.p + fz * P.dst.bstride + (size_t)xoA * BP;
+    const int wmask = P.wrap ? SMAX : 0x7fffffff;
+    const float factor = (float)SMAX;
 
     float hist[3][NOUT][CH];
 #pragma unroll
@@ -354,15 +360,22 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 if (RA) o[c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
                 else o[c] = max(trunc_i(fmaxf(__fmul_rn(t, factor), -1.0f)), 0) & wmask;
             }
-            const uint32_t pw = pack4_u8(o[0], CH > 1 ? o[CH - 1] : 0, 0, 0);      // saturating
-            if (CH == 1) orow[lane + 32 * i] = (uint8_t)pw;
-            else reinterpret_cast<unsigned short *>(orow)[lane + 32 * i] = (unsigned short)pw;
+            const int oi = lane + 32 * i;
+            if (SBITS == 8) {
+                const uint32_t pw = pack4_u8(o[0], o[CH - 1], 0, 0);      // saturating
+                if (CH == 1) orow[oi] = (uint8_t)pw;
+                else reinterpret_cast<unsigned short *>(orow)[oi] = (unsigned short)pw;
+            } else {
+                const uint32_t pw = pack2_u16(o[0], o[CH - 1]);
+                if (CH == 1) reinterpret_cast<unsigned short *>(orow)[oi] = (unsigned short)pw;
+                else reinterpret_cast<uint32_t *>(orow)[oi] = pw;
+            }
         }
         __syncwarp();
         uint8_t *prow = pd0 + (size_t)yo * pitch_d;
-        const int nbytes = nout * CH;
+        const int nbytes = nout * BP;
 #pragma unroll
-        for (int t = 0; t < (NOUT * CH + 3) / 4; t++) {
+        for (int t = 0; t < (NOUT * BP + 3) / 4; t++) {
             const int wd = lane + 32 * t;
             if (4 * wd + 3 < nbytes) stg32(prow + 4 * wd, reinterpret_cast<const uint32_t *>(orow)[wd]);
             else {
@@ -376,7 +389,7 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
         else pend1 = 0x7fffffff;
     };
 
-    // bank-conflict-free publication: as in the yuv kernel, lane l walks its 4 column pairs in the order j + rot
+    // bank-conflict-free publication: as in the yuv kernel, lane l walks its 4 pixel pairs in the order j + rot
     const int rot = (lane >> 1) & 3;
     f2 *wpos[4];
 #pragma unroll
@@ -387,39 +400,44 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
         if (RA) return add2(pk(mt, mb), bc(-GMATB_MAGIC));
         return norm2_inrange(mt, mb, P.nk);
     };
-    auto step = [&](const Rows &now, int kp) {
-        // bytes of this lane's 8 pixels, rotated by 2 rot pixels
-        uint32_t wt[2 * CH], wb[2 * CH];
-#pragma unroll
-        for (int k = 0; k < 2 * CH; k++) { wt[k] = now.t[k]; wb[k] = now.b[k]; }
-        if (CH == 1) {
+    // rotate a lane's 8 pixels left by 2 rot pixels, in its raw words
+    auto rotate = [&](uint32_t (&w)[NW]) {
+        if (NW == 2) {                                 // 8-bit, 1 component: a pair is 16 bits
             const int bits = 16 * rot;
-            const uint32_t tl = (bits & 32) ? wt[1] : wt[0], th = (bits & 32) ? wt[0] : wt[1];
-            const uint32_t bl = (bits & 32) ? wb[1] : wb[0], bh = (bits & 32) ? wb[0] : wb[1];
-            wt[0] = __funnelshift_r(tl, th, bits & 31); wt[1] = __funnelshift_r(th, tl, bits & 31);
-            wb[0] = __funnelshift_r(bl, bh, bits & 31); wb[1] = __funnelshift_r(bh, bl, bits & 31);
-        } else {                                       // 4 words of 2 pixels each: rotate whole words
-            uint32_t a[4], b[4];
+            const uint32_t lo = (bits & 32) ? w[1] : w[0], hi = (bits & 32) ? w[0] : w[1];
+            w[0] = __funnelshift_r(lo, hi, bits & 31); w[1] = __funnelshift_r(hi, lo, bits & 31);
+        } else {                                       // a pair is NW / 4 whole words: two conditional stages
+            uint32_t a[NW];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { a[k] = wt[k]; b[k] = wb[k]; }
+            for (int k = 0; k < NW; k++) a[k] = (rot & 2) ? w[(k + NW / 2) % NW] : w[k];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                wt[k] = rot == 0 ? a[k] : rot == 1 ? a[(k + 1) & 3] : rot == 2 ? a[(k + 2) & 3] : a[(k + 3) & 3];
-                wb[k] = rot == 0 ? b[k] : rot == 1 ? b[(k + 1) & 3] : rot == 2 ? b[(k + 2) & 3] : b[(k + 3) & 3];
-            }
+            for (int k = 0; k < NW; k++) w[k] = (rot & 1) ? a[(k + NW / 4) % NW] : a[k];
         }
+    };
+    auto step = [&](const Rows &now, int kp) {
+        uint32_t wt[NW], wb[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) { wt[k] = now.t[k]; wb[k] = now.b[k]; }
+        rotate(wt); rotate(wb);
         __syncwarp();                                  // the previous step's taps have been read
 #pragma unroll
         for (int j = 0; j < 4; j++) {                  // pixels 2j, 2j+1 (after rotation)
             f2 S[2][CH];
-            if (CH == 1) {
+            if (SBITS == 8 && CH == 1) {
                 const uint32_t a = wt[j >> 1], b = wb[j >> 1];
                 if (j & 1) { S[0][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][0] = sample2(byte_magic<3>(a), byte_magic<3>(b)); }
                 else       { S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[1][0] = sample2(byte_magic<1>(a), byte_magic<1>(b)); }
-            } else {
+            } else if (SBITS == 8) {                   // one word: c0 c1 of pixel 2j, c0 c1 of pixel 2j+1
                 const uint32_t a = wt[j], b = wb[j];
                 S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[0][CH - 1] = sample2(byte_magic<1>(a), byte_magic<1>(b));
                 S[1][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][CH - 1] = sample2(byte_magic<3>(a), byte_magic<3>(b));
+            } else if (CH == 1) {                      // one word: pixels 2j, 2j+1 as halves
+                const uint32_t a = wt[j], b = wb[j];
+                S[0][0] = sample2(half_magic<0>(a), half_magic<0>(b)); S[1][0] = sample2(half_magic<1>(a), half_magic<1>(b));
+            } else {                                   // two words: (c0, c1) of pixel 2j, (c0, c1) of pixel 2j+1
+                const uint32_t a0 = wt[(2 * j) % NW], b0 = wb[(2 * j) % NW], a1 = wt[(2 * j + 1) % NW], b1 = wb[(2 * j + 1) % NW];
+                S[0][0] = sample2(half_magic<0>(a0), half_magic<0>(b0)); S[0][CH - 1] = sample2(half_magic<1>(a0), half_magic<1>(b0));
+                S[1][0] = sample2(half_magic<0>(a1), half_magic<0>(b1)); S[1][CH - 1] = sample2(half_magic<1>(a1), half_magic<1>(b1));
             }
             if (lane < nconv) {
 #pragma unroll

@@ -63,7 +63,7 @@ def test_stream_full_sizes(dev, sw, sh, dw, dh):
                                          (32, 32, 14, 10), (200, 120, 24, 14), (500, 68, 2000, 70), (2000, 72, 500, 144), (1054, 126, 666, 80),
                                          (3840, 32, 1280, 12), (1440, 100, 48, 100), (48, 100, 1440, 100), (36, 4, 14, 6)])
 def test_plane_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):
-    for fmt, wrap in ((FMT.NV12, 0), (FMT.YUV420P, SWS.PARITY_WRAP)):
+    for fmt, wrap in ((FMT.NV12, 0), (FMT.YUV420P, SWS.PARITY_WRAP), (FMT.P016LE, 0), (FMT.YUV420P16LE, SWS.PARITY_WRAP), (FMT.P010LE, 0)):
         _, _, a = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, seed=sw + dh)
         _, _, b = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
         if not torch.equal(a.buf, b.buf):

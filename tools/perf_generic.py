@@ -31,3 +31,11 @@ for (sw, sh, dw, dh, B) in ((3840, 2160, 1920, 1080, 32), (1920, 1080, 1280, 720
             c = SwsContext(sw, sh, FMT.NV12, dw, dh, FMT.NV12, fl | SWS.HWACCEL_CUDA | extra, par)
             ms = timeit(lambda: c.scale(src, dst))
             print(f"nv12->nv12 {sw}x{sh}->{dw}x{dh} {name:9s} {kname:6s}: {ms:.3f} ms {B*sw*sh/ms/1e6:7.1f} Gpx/s(src) {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/PEAK*100:5.1f}%", flush=True)
+for (sw, sh, dw, dh, B) in ((3840, 2160, 1920, 1080, 32), (1920, 1080, 1280, 720, 64)):
+    src = FrameBatch(FMT.P010LE, sw, sh, B, device=dev); src.buf.random_(0, 256)
+    dst = FrameBatch(FMT.P010LE, dw, dh, B, device=dev)
+    alg = B * (sw * sh * 3.0 + dw * dh * 3.0)
+    for kname, extra in (("stream", 0), ("tile", SWS.TILE_KERNEL)):
+        c = SwsContext(sw, sh, FMT.P010LE, dw, dh, FMT.P010LE, SWS.BICUBIC | SWS.HWACCEL_CUDA | extra)
+        ms = timeit(lambda: c.scale(src, dst))
+        print(f"p010->p010 {sw}x{sh}->{dw}x{dh} bicubic   {kname:6s}: {ms:.3f} ms {B*sw*sh/ms/1e6:7.1f} Gpx/s(src) {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/PEAK*100:5.1f}%", flush=True)
