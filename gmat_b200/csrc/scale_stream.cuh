@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
     // ---- destination ------------------------------------------------------------------------------------------
     const unsigned pitch_d = F.dst.pl[0].pitch;
     uint8_t *pd0 = F.dst.pl[0].p + fz * F.dst.pl[0].bstride + (size_t)xoA * BPP;
-    const int wmask = P.wrap ? 0xFF : 0x7fffffff;      // GMATB_SWS_PARITY_WRAP: values >= 256 wrap instead of saturating
     // rgb24: lane q of a quad stores word q of the quad's 12 bytes (q < 3): bytes from its own pixel and the next lane's
     const int q = lane & 3;
     const uint32_t selq = q == 0 ? 0x4210u : q == 1 ? 0x5421u : 0x6542u;
@@ -122,27 +121,35 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
         const float4 w = wy0;
         uint8_t *prow = pd0 + (size_t)yo * pitch_d;
         uint32_t pw[NOUT];
+        int o[NOUT][4];
 #pragma unroll
         for (int i = 0; i < NOUT; i++) {
-            int o[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 // R-A weights are (0, 1-f, f, 0): FFMA(0, p, t) = t exactly, so the outer taps are skipped, not changed
                 const float t = RA ? __fmaf_rn(w.z, r2[i][c], __fmul_rn(w.y, r1[i][c]))
                                    : gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
                 // R-A: rint + saturate: 1.5 * 2^23 + t rounds to nearest even, its low bits are the integer; the pack saturates
-                if (RA) o[c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
-                // fmaxf(NaN, -1) = -1: a NaN (0/0 Lanczos coefficients, scale_generic.cuh) stores 0 like cvt.rzi.u32.f32
-                else o[c] = max(trunc_i(fmaxf(__fmul_rn(t, F.factor), -1.0f)), 0) & wmask;    // the pack saturates the rest
+                if (RA) o[i][c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
+                // fmaxf(NaN, -1) = -1: a NaN (0/0 Lanczos coefficients, scale_generic.cuh) stores 0 like cvt.rzi.u32.f32;
+                // negative values are sign-magnitude integers < 0: the saturating pack clamps both ends
+                else o[i][c] = trunc_i(fmaxf(__fmul_rn(t, F.factor), -1.0f));
             }
-            int a = 255;
+            o[i][3] = 255;
             if (BPP == 4) {
                 const float av = gen_chain(w.x, w.y, w.z, w.w, ah[i], ah[i], ah[i], ah[i]);
-                if (RA) a = __float_as_int(__fadd_rn(av, 12582912.0f)) - 0x4B400000;
-                else a = max(trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f)), 0) & wmask;
+                if (RA) o[i][3] = __float_as_int(__fadd_rn(av, 12582912.0f)) - 0x4B400000;
+                else o[i][3] = trunc_i(fmaxf(__fmul_rn(av, F.factor), -1.0f));
             }
-            pw[i] = pack4_u8(SW ? o[2] : o[0], o[1], SW ? o[0] : o[2], a);      // saturating
         }
+        if (!RA && P.wrap) {                          // GMATB_SWS_PARITY_WRAP (tests): values >= 256 wrap instead of saturating
+#pragma unroll
+            for (int i = 0; i < NOUT; i++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) o[i][c] = max(o[i][c], 0) & 0xFF;
+        }
+#pragma unroll
+        for (int i = 0; i < NOUT; i++) pw[i] = pack4_u8(SW ? o[i][2] : o[i][0], o[i][1], SW ? o[i][0] : o[i][2], o[i][3]);      // saturating
 #pragma unroll
         for (int i = 0; i < NOUT; i++) {
             const int oi = out_index(i);                               // index of the pixel among the warp's outputs
@@ -333,7 +340,6 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
         load_row(ps + rt * pitch_s, R.t); load_row(ps + rb * pitch_s, R.b);
     };
     uint8_t *pd0 = P.dst.p + fz * P.dst.bstride + (size_t)xoA * BP;
-    const int wmask = P.wrap ? SMAX : 0x7fffffff;
     const float factor = (float)SMAX;
 
     float hist[3][NOUT][CH];
@@ -358,7 +364,8 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 const float t = RA ? __fmaf_rn(w.z, r2[i][c], __fmul_rn(w.y, r1[i][c]))
                                    : gen_chain(w.x, w.y, w.z, w.w, r0[i][c], r1[i][c], r2[i][c], r3[i][c]);
                 if (RA) o[c] = __float_as_int(__fadd_rn(t, 12582912.0f)) - 0x4B400000;
-                else o[c] = max(trunc_i(fmaxf(__fmul_rn(t, factor), -1.0f)), 0) & wmask;
+                else o[c] = trunc_i(fmaxf(__fmul_rn(t, factor), -1.0f));
+                if (!RA && P.wrap) o[c] = max(o[c], 0) & SMAX;      // GMATB_SWS_PARITY_WRAP (tests)
             }
             const int oi = lane + 32 * i;
             if (SBITS == 8) {
