@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(256) rotate_linear4_kernel(PImg s, PImg d, Rot
 // rotate4_global.  Same arithmetic, same bytes.
 // The source position is monotonic in x and in y (correctly rounded operations of fixed operands), so the extremes
 // over the tile are at its corners, computed with the per-pixel formula itself.
+#ifndef GMATB_ROT_MINB
+#define GMATB_ROT_MINB 4
+#endif
 template <int BPP>
 __device__ __forceinline__ void rot_fetch2_smem(const uint8_t *tile, uint32_t off, float (&pa)[BPP], float (&pb)[BPP]) {
     const uint32_t *q = reinterpret_cast<const uint32_t *>(tile) + (off >> 2);
@@ -173,7 +176,7 @@ __device__ __forceinline__ void rot_fetch2_smem(const uint8_t *tile, uint32_t of
 }
 
 template <int BPP>
-__global__ void __launch_bounds__(256) rotate_linear_tma_kernel(const __grid_constant__ CUtensorMap smap, PImg s, PImg d, RotParams R,
+__global__ void __launch_bounds__(256, GMATB_ROT_MINB) rotate_linear_tma_kernel(const __grid_constant__ CUtensorMap smap, PImg s, PImg d, RotParams R,
                                                                 int box_x, int box_y) {
     extern __shared__ __align__(128) uint8_t rot_tile[];
     __shared__ uint64_t bar;
@@ -240,16 +243,16 @@ __global__ void __launch_bounds__(256) rotate_linear_tma_kernel(const __grid_con
         off[i] = (uint32_t)(y1 - by0) * (uint32_t)box_x + (uint32_t)(x1 * BPP - xb);
     }
     mbar_wait(&bar, 0);
-    float m[4][2][2][BPP];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        rot_fetch2_smem<BPP>(rot_tile, off[i], m[i][0][0], m[i][0][1]);
-        rot_fetch2_smem<BPP>(rot_tile, off[i] + (uint32_t)box_x, m[i][1][0], m[i][1][1]);
-    }
     if (!active) return;
     uint32_t ob[4][BPP];
 #pragma unroll
-    for (int i = 0; i < 4; i += 2) {
+    for (int i = 0; i < 4; i += 2) {                              // two pixels at a time: 8 taps of BPP floats live, not 16
+        float m[4][2][2][BPP];
+#pragma unroll
+        for (int k = i; k < i + 2; k++) {
+            rot_fetch2_smem<BPP>(rot_tile, off[k], m[k][0][0], m[k][0][1]);
+            rot_fetch2_smem<BPP>(rot_tile, off[k] + (uint32_t)box_x, m[k][1][0], m[k][1][1]);
+        }
         const f2 sx2 = pk(sx[i], sx[i + 1]), sy2 = pk(sy[i], sy[i + 1]);
         const f2 fx2 = pk(fx1[i], fx1[i + 1]), fy2 = pk(fy1[i], fy1[i + 1]);
         const f2 neg1 = bc(-1.0f);
