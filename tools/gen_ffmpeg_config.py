@@ -3,12 +3,13 @@
 config_components.h, libavutil/avconfig.h, libavutil/ffversion.h) for a
 C-only, x86-asm-free, swscale+avutil-only build of the reference tree.
 
-TEST INFRASTRUCTURE ONLY.  This is *our* recipe (the reference's own build
+BUILD SCAFFOLDING for this sandbox (the shim of gmat_b200/csrc/Makefile and the reference builds of oracle/refbuild);
+inside a real ffmpeg-gpu tree the headers come from its own configure.  This is *our* recipe (the reference's own build
 system is never run): every HAVE_/CONFIG_/ARCH_ token that the reference's
 libavutil / libswscale / compat sources mention is defined to 0, then a short
 whitelist describing this container (glibc, pthreads, gcc) is set to 1.
 
-usage: gen_config.py <reference ffmpeg-gpu dir> <output include dir> [avfilter]
+usage: gen_ffmpeg_config.py <reference ffmpeg-gpu dir> <output include dir> [avfilter]
 
 With `avfilter` the headers describe the AVFilter harness build instead (oracle/refbuild `avf`): libavfilter's
 tokens are scanned too and CONFIG_AVFILTER / CONFIG_CUDA / CONFIG_FFNVCODEC are on (hwcontext_cuda.c is compiled
@@ -97,7 +98,7 @@ def main():
         ones -= {"CONFIG_CVCUDA"}          # the nvcv filters / libgpuscale glue are what we replace; not compiled here
     os.makedirs(os.path.join(out, "libavutil"), exist_ok=True)
     with open(os.path.join(out, "config.h"), "w") as f:
-        f.write("/* generated by oracle/refbuild/gen_config.py -- not by the reference's configure */\n")
+        f.write("/* generated by tools/gen_ffmpeg_config.py -- not by the reference's configure */\n")
         f.write("#ifndef FFMPEG_CONFIG_H\n#define FFMPEG_CONFIG_H\n")
         for k, v in STRINGS.items():
             f.write(f"#define {k} {v}\n")

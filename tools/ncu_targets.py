@@ -30,7 +30,7 @@ if "generic" in which:
 a = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev); a.buf.random_(0, 256)
 b = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev)
 if "rotate" in which:
-    g.rotate(a, b, 30.0, 0.0, 0.0, INTERP.LINEAR)
+    g.rotate(a, b, 30.0, -282.7688, 1104.6926, INTERP.LINEAR)      # BASELINE C4: about the centre
 if "gauss" in which:
     g.gaussian(a, b, 5, 5, 1.1, 1.1, BORDER.REFLECT101)
 if "median" in which:
