@@ -10,6 +10,7 @@
 #include "scale_bilinear2.cuh"
 #include "scale_generic.cuh"
 #include "scale_stream.cuh"
+#include "scale_plane2.cuh"
 
 namespace gmatb {
 int yuv2rgb_launch(const GmatbImage *, const GmatbImage *, const Mat9 &, cudaStream_t);
@@ -78,6 +79,7 @@ struct GmatbSws {
     bool taps2;
     int iw;   // 0, or 1..3: both axes have the dyadic weights of the exact-integer kernel (scale_fused4i.cuh)
     // any-ratio streaming kernel (scale_stream.cuh): which strip / outputs each warp owns; built on first use
+    float pw2[2][8]; int pw2_state[2];      // exact-2:1 plane kernel (scale_plane2.cuh): the 4 + 4 weights per filter bank; 0 unknown, 1 ready
     int4 *splan[2]; int splan_n[2], splan_nout[2], splan_state[2];   // per filter bank; state: 0 not built, 1 ready, -1 does not apply
     // scratch
     void *tmp; size_t tmp_size;
@@ -123,6 +125,7 @@ extern "C" GmatbSws *gmatb_sws_create(int srcW, int srcH, int srcFormat, int dst
     c->tmp = c->stage_src = c->stage_dst = nullptr;
     c->tmp_size = c->stage_src_size = c->stage_dst_size = 0;
     c->pipe = nullptr;
+    c->pw2_state[0] = c->pw2_state[1] = 0;
     for (int i = 0; i < 2; i++) { c->splan[i] = nullptr; c->splan_n[i] = c->splan_nout[i] = c->splan_state[i] = 0; }
     c->srcW = srcW; c->srcH = srcH; c->srcFmt = srcFormat; c->dstW = dstW; c->dstH = dstH; c->dstFmt = dstFormat;
     c->flags = flags; c->cspace = colorspace; c->stream = 0;
@@ -551,6 +554,36 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     si.pl[0].p = (uint8_t *)s->data[plane]; si.pl[0].pitch = s->linesize[plane]; si.pl[0].bstride = s->batch > 1 ? s->batch_stride[plane] : 0;
     di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
+    // exactly 2:1, 8-bit, R-B: the register-streaming plane kernel (scale_plane2.cuh)
+    if (bits == 8 && (ch == 1 || ch == 2) && !c->ra && !(c->flags & GMATB_SWS_TILE_KERNEL) && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
+        planes_aligned(si, 1, 8 * ch) && planes_aligned(di, 1, 4 * ch)) {
+        if (!c->pw2_state[bank]) {
+            float4 hx, hy;
+            if (cudaMemcpy(&hx, c->cx[bank], sizeof(hx), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(&hy, c->cy[bank], sizeof(hy), cudaMemcpyDeviceToHost) != cudaSuccess) return set_cuda_error(cudaGetLastError());
+            const float w[8] = {hx.x, hx.y, hx.z, hx.w, hy.x, hy.y, hy.z, hy.w};
+            memcpy(c->pw2[bank], w, sizeof(w));
+            c->pw2_state[bank] = 1;
+        }
+        Plane2Params Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.src = si.pl[0]; Q.dst = di.pl[0];
+        Q.W = pw; Q.H = ph; Q.dstW = dw; Q.dstH = dh;
+        for (int i = 0; i < 4; i++) { Q.wx[i] = c->pw2[bank][i]; Q.wy[i] = c->pw2[bank][4 + i]; }
+        Q.nk = norm_k(8);
+        Q.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
+        const int batch = s->batch > 1 ? s->batch : 1;
+        const int warps_x = (pw / 8 + 29) / 30;
+        long long want = 148LL * 16 * 8;
+        int nb = (int)((want + (long long)warps_x * batch - 1) / ((long long)warps_x * batch));
+        nb = std::max(1, std::min(nb, (dh + 31) / 32));
+        Q.band = (dh + nb - 1) / nb;
+        nb = (dh + Q.band - 1) / Q.band;
+        dim3 g(warps_x, nb, batch);
+        if (ch == 1) plane_scale2_kernel<1><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2><<<g, 32, 0, c->stream>>>(Q);
+        count_launch();
+        return set_cuda_error(cudaGetLastError());
+    }
     // 8- and 16-bit planes of 1 or 2 components: the streaming kernel (scale_stream.cuh)
     const int bp = ch * bits / 8;
     if ((ch == 1 || ch == 2) && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->splan_state[bank] >= 0 &&

@@ -60,6 +60,8 @@ def test_stream_full_sizes(dev, sw, sh, dw, dh):
 # ---- yuv -> yuv: every plane through the plane form of the streaming kernel (what the scale_cuda filter runs) -----------
 @pytest.mark.parametrize("name,flag,param", ALGOS)
 @pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (3840, 2160, 1920, 1080), (640, 360, 1280, 720), (64, 48, 40, 30), (66, 34, 100, 58),
+                                         # exactly 2:1 (scale_plane2.cuh where the plane width is a multiple of 8; warp seams at 30 / 31 / 29 / 61 strips)
+                                         (64, 48, 32, 24), (16, 4, 8, 2), (512, 132, 256, 66), (480, 12, 240, 6), (496, 12, 248, 6), (464, 72, 232, 36), (976, 8, 488, 4), (248, 12, 124, 6), (1920, 1080, 960, 540),
                                          (32, 32, 14, 10), (200, 120, 24, 14), (500, 68, 2000, 70), (2000, 72, 500, 144), (1054, 126, 666, 80),
                                          (3840, 32, 1280, 12), (1440, 100, 48, 100), (48, 100, 1440, 100), (36, 4, 14, 6)])
 def test_plane_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):

@@ -25,6 +25,9 @@ if "bilinear" in which:
 if "stream" in which:
     s1080 = FrameBatch(FMT.NV12, 1920, 1080, B, device=dev); s1080.buf.random_(0, 256)
     SwsContext(1920, 1080, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | HW, (0.75,)).scale(s1080, d720)
+if "plane" in which:
+    dn = FrameBatch(FMT.NV12, 1920, 1080, B, device=dev)
+    SwsContext(3840, 2160, FMT.NV12, 1920, 1080, FMT.NV12, SWS.BICUBIC | HW).scale(src, dn)
 if "generic" in which:
     SwsContext(3840, 2160, FMT.NV12, 1280, 720, FMT.RGB24, SWS.BICUBIC | HW).scale(src, d720)
 a = FrameBatch(FMT.RGB24, 3840, 2160, B, device=dev); a.buf.random_(0, 256)
