@@ -463,7 +463,7 @@ def main():
                 ("1080p NV12 -> 720p RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (1920, 1080, 1280, 720), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
                 ("4K NV12 -> 720p RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (3840, 2160, 1280, 720), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
                 ("1080p NV12 -> 4K RGB24, bicubic R-B param0=0.75 (any-ratio streaming kernel)", (1920, 1080, 3840, 2160), FMT.NV12, FMT.RGB24, SWS.BICUBIC, (0.75,), 3.0),
-                ("4K NV12 -> 1080p NV12, bicubic R-B default parameter (plane streaming kernel: the scale_cuda filter's path)", (3840, 2160, 1920, 1080), FMT.NV12, FMT.NV12, SWS.BICUBIC, None, 1.5)):
+                ("4K NV12 -> 1080p NV12, bicubic R-B default parameter (exact-2:1 plane kernel: the scale_cuda filter's path)", (3840, 2160, 1920, 1080), FMT.NV12, FMT.NV12, SWS.BICUBIC, None, 1.5)):
             nb_ = 16 if bw > aw else 32
             sa = FrameBatch(afmt, aw, ah, nb_, device=dev); sa.buf.random_(0, 256)
             sb = FrameBatch(bfmt, bw, bh, nb_, device=dev)

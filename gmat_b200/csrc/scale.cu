@@ -554,9 +554,9 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     si.pl[0].p = (uint8_t *)s->data[plane]; si.pl[0].pitch = s->linesize[plane]; si.pl[0].bstride = s->batch > 1 ? s->batch_stride[plane] : 0;
     di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
-    // exactly 2:1, 8-bit, R-B: the register-streaming plane kernel (scale_plane2.cuh)
-    if (bits == 8 && (ch == 1 || ch == 2) && !c->ra && !(c->flags & GMATB_SWS_TILE_KERNEL) && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
-        planes_aligned(si, 1, 8 * ch) && planes_aligned(di, 1, 4 * ch)) {
+    // exactly 2:1, R-B: the register-streaming plane kernel (scale_plane2.cuh)
+    if ((ch == 1 || ch == 2) && !c->ra && !(c->flags & GMATB_SWS_TILE_KERNEL) && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
+        planes_aligned(si, 1, ch * bits == 8 ? 8 : 16) && planes_aligned(di, 1, std::min(16, 4 * ch * bits / 8))) {
         if (!c->pw2_state[bank]) {
             float4 hx, hy;
             if (cudaMemcpy(&hx, c->cx[bank], sizeof(hx), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -570,7 +570,7 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
         Q.src = si.pl[0]; Q.dst = di.pl[0];
         Q.W = pw; Q.H = ph; Q.dstW = dw; Q.dstH = dh;
         for (int i = 0; i < 4; i++) { Q.wx[i] = c->pw2[bank][i]; Q.wy[i] = c->pw2[bank][4 + i]; }
-        Q.nk = norm_k(8);
+        Q.nk = norm_k(bits);
         Q.wrap = (c->flags & GMATB_SWS_PARITY_WRAP) ? 1 : 0;
         const int batch = s->batch > 1 ? s->batch : 1;
         const int warps_x = (pw / 8 + 29) / 30;
@@ -580,7 +580,8 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
         Q.band = (dh + nb - 1) / nb;
         nb = (dh + Q.band - 1) / Q.band;
         dim3 g(warps_x, nb, batch);
-        if (ch == 1) plane_scale2_kernel<1><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2><<<g, 32, 0, c->stream>>>(Q);
+        if (bits == 8) { if (ch == 1) plane_scale2_kernel<1, 8><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2, 8><<<g, 32, 0, c->stream>>>(Q); }
+        else           { if (ch == 1) plane_scale2_kernel<1, 16><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2, 16><<<g, 32, 0, c->stream>>>(Q); }
         count_launch();
         return set_cuda_error(cudaGetLastError());
     }

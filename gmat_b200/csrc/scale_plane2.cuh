@@ -1,13 +1,13 @@
-// scale_plane2.cuh -- exact 2:1 four-tap resample of ONE 8-bit PLANE with CH = 1 or 2 interleaved components:
-// the Y / U / V planes of yuv420p and the Y / UV planes of nv12 in yuv -> yuv scaling at half size (4K -> 1080p,
+// scale_plane2.cuh -- exact 2:1 four-tap resample of ONE 8- or 16-bit PLANE with CH = 1 or 2 interleaved components:
+// the Y / U / V planes of yuv420p(16) and the Y / UV planes of nv12 / p010 / p016 in yuv -> yuv scaling at half size (4K -> 1080p,
 // 1080p -> 540p: the step of an ABR ladder; the scale_cuda filter's path and sws_scale's yuv -> yuv branch,
 // swscale_cuda.c:372-476).  The register-streaming layout of scale_fused3.cuh without the colour conversion:
 //   * one warp per CTA, a lane owns a strip of 8 source pixels (4 outputs) and walks down a band one row pair per
 //     step; loads two steps ahead; strips overlap by one lane per side, so halo columns are plain SHFL results;
-//   * samples p = RN(j / 255) as packed (top, bottom) pairs; the horizontal chain once per source row, the
+//   * samples p = RN(j / max) as packed (top, bottom) pairs; the horizontal chain once per source row, the
 //     vertical one as a running accumulation in the reference's operand order (resample_core.cuh): bit-identical
 //     to the tile and streaming kernels and to the reference's Subsample_* kernels;
-//   * a lane stores 4 (CH = 1) or 8 (CH = 2) bytes per output row, contiguous across the warp.
+//   * a lane stores its 4 output pixels (4 .. 16 bytes) per output row, contiguous across the warp.
 // Nothing but the source bytes is read and nothing but the destination written: 1.25 B per source sample, and
 // ~5.5 FP32 lane-operations -- unlike the colour-converting kernels this one can be HBM-bound.
 #pragma once
@@ -23,10 +23,12 @@ struct Plane2Params {
     int band, wrap;
 };
 
-template <int CH>
+template <int CH, int SBITS>
 __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_constant__ Plane2Params P) {
     constexpr int OWN = 30;
-    constexpr int NWD = 2 * CH;                                   // words of 8 pixels
+    constexpr int BP = CH * SBITS / 8;                            // bytes per pixel: 1, 2, 2, 4
+    constexpr int NWD = 2 * BP;                                   // words of 8 pixels
+    constexpr int SMAX = SBITS == 8 ? 255 : 65535;
     const int lane = threadIdx.x;
     const int nstrips = P.W >> 3;
     const int strip = blockIdx.x * OWN + lane - 1;
@@ -37,23 +39,32 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
     const long long fz = blockIdx.z;
     const int H = P.H;
     const int yo_begin = blockIdx.y * P.band, yo_end = min(yo_begin + P.band, P.dstH);
-    const uint8_t *ps = P.src.p + fz * P.src.bstride + (size_t)sl * (8 * CH);
+    const uint8_t *ps = P.src.p + fz * P.src.bstride + (size_t)sl * (8 * BP);
     const unsigned pitch_s = P.src.pitch, pitch_d = P.dst.pitch;
     // pair k finishes output row k-1 and starts row k: pairs yo_begin-1 .. yo_end; the first two only prime the accumulators
     const int kfirst = yo_begin - 1, klast = yo_end, kstore = kfirst + 2;
-    uint8_t *pd = P.dst.p + fz * P.dst.bstride + ((long long)kfirst - 1) * (long long)pitch_d + (long long)(owner ? strip : 0) * (4 * CH);
+    uint8_t *pd = P.dst.p + fz * P.dst.bstride + ((long long)kfirst - 1) * (long long)pitch_d + (long long)(owner ? strip : 0) * (4 * BP);
 
     struct Rows { uint32_t t[NWD], b[NWD]; };
     auto load_row = [&](const uint8_t *q, uint32_t (&w)[NWD]) {
-        if (CH == 1) { const uint2 a = ldg64(q); w[0] = a.x; w[1] = a.y; }
-        else { const uint4 a = ldg128(q); w[0] = a.x; w[1] = a.y; w[NWD - 2] = a.z; w[NWD - 1] = a.w; }
-        if (edge) {
-            if (CH == 1) {
-                if (lrep) w[1] = prmt(w[1], w[0], 0x4210u);              // pixel 7 := pixel 0
-                if (rrep) w[0] = prmt(w[0], w[1], 0x3217u);              // pixel 0 := pixel 7
-            } else {
-                if (lrep) w[NWD - 1] = prmt(w[NWD - 1], w[0], 0x5410u);  // pixel 7 (upper half of the last word) := pixel 0
-                if (rrep) w[0] = prmt(w[0], w[NWD - 1], 0x3276u);        // pixel 0 := pixel 7
+        if (NWD == 2) { const uint2 a = ldg64(q); w[0] = a.x; w[1] = a.y; }
+        else {
+#pragma unroll
+            for (int i = 0; i < NWD / 4; i++) {
+                const uint4 a = ldg128(q + 16 * i);
+                w[4 * i] = a.x; w[4 * i + 1] = a.y; w[(4 * i + 2) % NWD] = a.z; w[(4 * i + 3) % NWD] = a.w;
+            }
+        }
+        if (edge) {                              // out-of-frame provider strips: pixel 7 := pixel 0 (left), pixel 0 := pixel 7 (right)
+            if (BP == 1) {
+                if (lrep) w[1] = prmt(w[1], w[0], 0x4210u);
+                if (rrep) w[0] = prmt(w[0], w[1], 0x3217u);
+            } else if (BP == 2) {                // a pixel is half a word
+                if (lrep) w[NWD - 1] = prmt(w[NWD - 1], w[0], 0x5410u);
+                if (rrep) w[0] = prmt(w[0], w[NWD - 1], 0x3276u);
+            } else {                             // a pixel is a word
+                if (lrep) w[NWD - 1] = w[0];
+                if (rrep) w[0] = w[NWD - 1];
             }
         }
     };
@@ -73,14 +84,20 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
         f2 C[8][CH];
 #pragma unroll
         for (int x = 0; x < 8; x++) {
-            if (CH == 1) {
+            if (BP == 1) {
                 const uint32_t a = now.t[x >> 2], b = now.b[x >> 2];
                 C[x][0] = (x & 3) == 0 ? norm2_inrange(byte_magic<0>(a), byte_magic<0>(b), P.nk) : (x & 3) == 1 ? norm2_inrange(byte_magic<1>(a), byte_magic<1>(b), P.nk)
                         : (x & 3) == 2 ? norm2_inrange(byte_magic<2>(a), byte_magic<2>(b), P.nk) : norm2_inrange(byte_magic<3>(a), byte_magic<3>(b), P.nk);
-            } else {
+            } else if (SBITS == 8) {             // 2 components of 8 bits: a word is two pixels
                 const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
                 if (x & 1) { C[x][0] = norm2_inrange(byte_magic<2>(a), byte_magic<2>(b), P.nk); C[x][CH - 1] = norm2_inrange(byte_magic<3>(a), byte_magic<3>(b), P.nk); }
                 else       { C[x][0] = norm2_inrange(byte_magic<0>(a), byte_magic<0>(b), P.nk); C[x][CH - 1] = norm2_inrange(byte_magic<1>(a), byte_magic<1>(b), P.nk); }
+            } else if (CH == 1) {                // 1 component of 16 bits: a word is two pixels
+                const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
+                C[x][0] = (x & 1) ? norm2_inrange(half_magic<1>(a), half_magic<1>(b), P.nk) : norm2_inrange(half_magic<0>(a), half_magic<0>(b), P.nk);
+            } else {                             // 2 components of 16 bits: a word is one pixel
+                const uint32_t a = now.t[x % NWD], b = now.b[x % NWD];
+                C[x][0] = norm2_inrange(half_magic<0>(a), half_magic<0>(b), P.nk); C[x][CH - 1] = norm2_inrange(half_magic<1>(a), half_magic<1>(b), P.nk);
             }
         }
         f2 PL[CH], PR[CH];
@@ -102,11 +119,13 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     const float v = __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
-                    o[xo][c] = trunc_i(__fmul_rn(v, 255.0f));
-                    if (P.wrap) o[xo][c] = max(o[xo][c], 0) & 0xFF;
+                    o[xo][c] = trunc_i(__fmul_rn(v, (float)SMAX));
+                    if (P.wrap) o[xo][c] = max(o[xo][c], 0) & SMAX;
                 }
-            if (CH == 1) stg32(pd, pack4_u8(o[0][0], o[1][0], o[2][0], o[3][0]));
-            else stg64(pd, make_uint2(pack4_u8(o[0][0], o[0][CH - 1], o[1][0], o[1][CH - 1]), pack4_u8(o[2][0], o[2][CH - 1], o[3][0], o[3][CH - 1])));
+            if (BP == 1) stg32(pd, pack4_u8(o[0][0], o[1][0], o[2][0], o[3][0]));
+            else if (SBITS == 8) stg64(pd, make_uint2(pack4_u8(o[0][0], o[0][CH - 1], o[1][0], o[1][CH - 1]), pack4_u8(o[2][0], o[2][CH - 1], o[3][0], o[3][CH - 1])));
+            else if (CH == 1) stg64(pd, make_uint2(pack2_u16(o[0][0], o[1][0]), pack2_u16(o[2][0], o[3][0])));
+            else stg128(pd, make_uint4(pack2_u16(o[0][0], o[0][CH - 1]), pack2_u16(o[1][0], o[1][CH - 1]), pack2_u16(o[2][0], o[2][CH - 1]), pack2_u16(o[3][0], o[3][CH - 1])));
         }
 #pragma unroll
         for (int xo = 0; xo < 4; xo++)
