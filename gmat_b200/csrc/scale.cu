@@ -555,7 +555,8 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     di.pl[0].p = (uint8_t *)d->data[plane]; di.pl[0].pitch = d->linesize[plane]; di.pl[0].bstride = d->batch > 1 ? d->batch_stride[plane] : 0;
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
     // exactly 2:1, R-B: the register-streaming plane kernel (scale_plane2.cuh)
-    if ((ch == 1 || ch == 2) && !c->ra && !(c->flags & GMATB_SWS_TILE_KERNEL) && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
+    // (its taps are at 2 o - 1 .. 2 o + 2 on both axes: true of bicubic / Lanczos / bilinear at 2:1, not of nearest)
+    if ((ch == 1 || ch == 2) && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->algo != RS_NEAREST && c->hpx[bank][0] == -1 && c->hpy[bank][0] == -1 && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
         planes_aligned(si, 1, ch * bits == 8 ? 8 : 16) && planes_aligned(di, 1, std::min(16, 4 * ch * bits / 8))) {
         if (!c->pw2_state[bank]) {
             float4 hx, hy;
@@ -580,8 +581,10 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
         Q.band = (dh + nb - 1) / nb;
         nb = (dh + Q.band - 1) / Q.band;
         dim3 g(warps_x, nb, batch);
-        if (bits == 8) { if (ch == 1) plane_scale2_kernel<1, 8><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2, 8><<<g, 32, 0, c->stream>>>(Q); }
-        else           { if (ch == 1) plane_scale2_kernel<1, 16><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<2, 16><<<g, 32, 0, c->stream>>>(Q); }
+#define P2(C_, B_) do { if (c->ra) plane_scale2_kernel<C_, B_, 1><<<g, 32, 0, c->stream>>>(Q); else plane_scale2_kernel<C_, B_, 0><<<g, 32, 0, c->stream>>>(Q); } while (0)
+        if (bits == 8) { if (ch == 1) P2(1, 8); else P2(2, 8); }
+        else           { if (ch == 1) P2(1, 16); else P2(2, 16); }
+#undef P2
         count_launch();
         return set_cuda_error(cudaGetLastError());
     }

@@ -23,7 +23,7 @@ struct Plane2Params {
     int band, wrap;
 };
 
-template <int CH, int SBITS>
+template <int CH, int SBITS, int RA>
 __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_constant__ Plane2Params P) {
     constexpr int OWN = 30;
     constexpr int BP = CH * SBITS / 8;                            // bytes per pixel: 1, 2, 2, 4
@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
 #pragma unroll
         for (int c = 0; c < CH; c++) { acc[i][c] = 0.f; hb_prev[i][c] = 0.f; }
 
+    // (top, bottom) magic floats -> the samples: RN(j / max) (R-B) or j (R-A: SWS_BILINEAR / SWS_POINT)
+    auto smp = [&](float mt, float mb) -> f2 { return RA ? add2(pk(mt, mb), bc(-GMATB_MAGIC)) : norm2_inrange(mt, mb, P.nk); };
     auto step = [&](const Rows &now, bool store) {
         // the 8 columns as (top, bottom) sample pairs
         f2 C[8][CH];
@@ -86,18 +88,18 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
         for (int x = 0; x < 8; x++) {
             if (BP == 1) {
                 const uint32_t a = now.t[x >> 2], b = now.b[x >> 2];
-                C[x][0] = (x & 3) == 0 ? norm2_inrange(byte_magic<0>(a), byte_magic<0>(b), P.nk) : (x & 3) == 1 ? norm2_inrange(byte_magic<1>(a), byte_magic<1>(b), P.nk)
-                        : (x & 3) == 2 ? norm2_inrange(byte_magic<2>(a), byte_magic<2>(b), P.nk) : norm2_inrange(byte_magic<3>(a), byte_magic<3>(b), P.nk);
+                C[x][0] = (x & 3) == 0 ? smp(byte_magic<0>(a), byte_magic<0>(b)) : (x & 3) == 1 ? smp(byte_magic<1>(a), byte_magic<1>(b))
+                        : (x & 3) == 2 ? smp(byte_magic<2>(a), byte_magic<2>(b)) : smp(byte_magic<3>(a), byte_magic<3>(b));
             } else if (SBITS == 8) {             // 2 components of 8 bits: a word is two pixels
                 const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
-                if (x & 1) { C[x][0] = norm2_inrange(byte_magic<2>(a), byte_magic<2>(b), P.nk); C[x][CH - 1] = norm2_inrange(byte_magic<3>(a), byte_magic<3>(b), P.nk); }
-                else       { C[x][0] = norm2_inrange(byte_magic<0>(a), byte_magic<0>(b), P.nk); C[x][CH - 1] = norm2_inrange(byte_magic<1>(a), byte_magic<1>(b), P.nk); }
+                if (x & 1) { C[x][0] = smp(byte_magic<2>(a), byte_magic<2>(b)); C[x][CH - 1] = smp(byte_magic<3>(a), byte_magic<3>(b)); }
+                else       { C[x][0] = smp(byte_magic<0>(a), byte_magic<0>(b)); C[x][CH - 1] = smp(byte_magic<1>(a), byte_magic<1>(b)); }
             } else if (CH == 1) {                // 1 component of 16 bits: a word is two pixels
                 const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
-                C[x][0] = (x & 1) ? norm2_inrange(half_magic<1>(a), half_magic<1>(b), P.nk) : norm2_inrange(half_magic<0>(a), half_magic<0>(b), P.nk);
+                C[x][0] = (x & 1) ? smp(half_magic<1>(a), half_magic<1>(b)) : smp(half_magic<0>(a), half_magic<0>(b));
             } else {                             // 2 components of 16 bits: a word is one pixel
                 const uint32_t a = now.t[x % NWD], b = now.b[x % NWD];
-                C[x][0] = norm2_inrange(half_magic<0>(a), half_magic<0>(b), P.nk); C[x][CH - 1] = norm2_inrange(half_magic<1>(a), half_magic<1>(b), P.nk);
+                C[x][0] = smp(half_magic<0>(a), half_magic<0>(b)); C[x][CH - 1] = smp(half_magic<1>(a), half_magic<1>(b));
             }
         }
         f2 PL[CH], PR[CH];
@@ -119,8 +121,11 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     const float v = __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
-                    o[xo][c] = trunc_i(__fmul_rn(v, (float)SMAX));
-                    if (P.wrap) o[xo][c] = max(o[xo][c], 0) & SMAX;
+                    if (RA) o[xo][c] = __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;      // rint; the pack saturates
+                    else {
+                        o[xo][c] = trunc_i(__fmul_rn(v, (float)SMAX));
+                        if (P.wrap) o[xo][c] = max(o[xo][c], 0) & SMAX;
+                    }
                 }
             if (BP == 1) stg32(pd, pack4_u8(o[0][0], o[1][0], o[2][0], o[3][0]));
             else if (SBITS == 8) stg64(pd, make_uint2(pack4_u8(o[0][0], o[0][CH - 1], o[1][0], o[1][CH - 1]), pack4_u8(o[2][0], o[2][CH - 1], o[3][0], o[3][CH - 1])));
