@@ -278,7 +278,7 @@ int fused_int_launch(bool semi, int dc, int iw, bool wrap, dim3 g, cudaStream_t 
 int fused_mma_launch(int dc, int iw, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P);
 // any-ratio streaming kernel (8-bit yuv -> 8-bit packed rgb): scale_stream.cu
 int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStream_t st, const StreamParams &P);
-int plane_stream_launch(int ch, int bits, int nout, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P);
+int plane_stream_launch(int ch, int bits, int nout, int deal, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P);
 
 static bool planes_aligned(const Img &a, int np, int al) {
     for (int i = 0; i < np; i++)
@@ -608,7 +608,9 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
             nb = std::max(1, std::min(nb, (dh + 15) / 16));
             P.band = (dh + nb - 1) / nb;
             nb = (dh + P.band - 1) / P.band;
-            return plane_stream_launch(ch, bits, c->splan_nout[bank], c->ra ? 1 : 0, dim3(c->splan_n[bank], nb, batch), c->stream, P);
+            const double r = (double)pw / dw;
+            const int deal = (c->splan_nout[bank] == 5 && r >= 1.25 && r <= 1.75) ? 1 : 0;
+            return plane_stream_launch(ch, bits, c->splan_nout[bank], deal, c->ra ? 1 : 0, dim3(c->splan_n[bank], nb, batch), c->stream, P);
         }
     }
     return run_generic(c, bank, si, di, dw, dh, GS_PACKED, ch, bits, 0, s->batch);

@@ -297,7 +297,7 @@ struct PlaneStreamParams {
     int band, wrap;
 };
 
-template <int CH, int SBITS, int NOUT, int RA, int MINB>
+template <int CH, int SBITS, int NOUT, int DEAL, int RA, int MINB>
 __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __grid_constant__ PlaneStreamParams P) {
     constexpr int BP = CH * SBITS / 8;                // bytes per pixel: 1, 2, 2, 4
     constexpr int NW = 2 * BP;                        // words of a lane's 8 pixels
@@ -309,11 +309,15 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
     const int W = P.W, H = P.H;
     const int4 pl = P.plan[blockIdx.x];
     const int X0 = pl.x, xoA = pl.y, nout = pl.z, nconv = pl.w;
+    // DEAL 1 (NOUT = 5, ratios near 1.5): outputs 2 lane, 2 lane + 1, 64 + the same, 128 + lane -- an odd lane stride in the
+    // row buffer, no LDS bank conflicts (see the yuv kernel)
+    auto out_index = [&](int i) { return DEAL == 0 ? lane + 32 * i : i < 4 ? 64 * (i >> 1) + 2 * lane + (i & 1) : 128 + lane; };
+    static_assert(DEAL == 0 || NOUT == 5, "the paired deal is laid out for 5 outputs per lane");
     float4 wx[NOUT];
     int off[NOUT];
 #pragma unroll
     for (int i = 0; i < NOUT; i++) {
-        const int xo = xoA + min(lane + 32 * i, nout - 1);
+        const int xo = xoA + min(out_index(i), nout - 1);
         wx[i] = __ldg(P.cx + xo);
         off[i] = __ldg(P.px + xo) - X0 + 2;
     }
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 else o[c] = trunc_i(fmaxf(__fmul_rn(t, factor), -1.0f));
                 if (!RA && P.wrap) o[c] = max(o[c], 0) & SMAX;      // GMATB_SWS_PARITY_WRAP (tests)
             }
-            const int oi = lane + 32 * i;
+            const int oi = out_index(i);
             if (SBITS == 8) {
                 const uint32_t pw = pack4_u8(o[0], o[CH - 1], 0, 0);      // saturating
                 if (CH == 1) orow[oi] = (uint8_t)pw;
