@@ -1,4 +1,5 @@
-// scale_plane2.cuh -- exact 2:1 four-tap resample of ONE 8- or 16-bit PLANE with CH = 1 or 2 interleaved components:
+// scale_plane2.cuh -- exact 2:1 four-tap resample of ONE 8- or 16-bit PLANE with CH = 1 or 2 interleaved components (or 4 of
+// 8 bits: rgb0 / bgr0 / rgba / bgra):
 // the Y / U / V planes of yuv420p(16) and the Y / UV planes of nv12 / p010 / p016 in yuv -> yuv scaling at half size (4K -> 1080p,
 // 1080p -> 540p: the step of an ABR ladder; the scale_cuda filter's path and sws_scale's yuv -> yuv branch,
 // swscale_cuda.c:372-476).  The register-streaming layout of scale_fused3.cuh without the colour conversion:
@@ -24,7 +25,7 @@ struct Plane2Params {
 };
 
 template <int CH, int SBITS, int RA>
-__global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_constant__ Plane2Params P) {
+__global__ void __launch_bounds__(32, CH == 4 ? 12 : 16) plane_scale2_kernel(const __grid_constant__ Plane2Params P) {
     constexpr int OWN = 30;
     constexpr int BP = CH * SBITS / 8;                            // bytes per pixel: 1, 2, 2, 4
     constexpr int NWD = 2 * BP;                                   // words of 8 pixels
@@ -90,10 +91,14 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
                 const uint32_t a = now.t[x >> 2], b = now.b[x >> 2];
                 C[x][0] = (x & 3) == 0 ? smp(byte_magic<0>(a), byte_magic<0>(b)) : (x & 3) == 1 ? smp(byte_magic<1>(a), byte_magic<1>(b))
                         : (x & 3) == 2 ? smp(byte_magic<2>(a), byte_magic<2>(b)) : smp(byte_magic<3>(a), byte_magic<3>(b));
-            } else if (SBITS == 8) {             // 2 components of 8 bits: a word is two pixels
+            } else if (SBITS == 8 && CH == 2) {  // 2 components of 8 bits: a word is two pixels
                 const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
                 if (x & 1) { C[x][0] = smp(byte_magic<2>(a), byte_magic<2>(b)); C[x][CH - 1] = smp(byte_magic<3>(a), byte_magic<3>(b)); }
                 else       { C[x][0] = smp(byte_magic<0>(a), byte_magic<0>(b)); C[x][CH - 1] = smp(byte_magic<1>(a), byte_magic<1>(b)); }
+            } else if (SBITS == 8 && CH == 4) {  // 4 components of 8 bits: a word is one pixel
+                const uint32_t a = now.t[x % NWD], b = now.b[x % NWD];
+                C[x][0] = smp(byte_magic<0>(a), byte_magic<0>(b)); C[x][1 % CH] = smp(byte_magic<1>(a), byte_magic<1>(b));
+                C[x][2 % CH] = smp(byte_magic<2>(a), byte_magic<2>(b)); C[x][3 % CH] = smp(byte_magic<3>(a), byte_magic<3>(b));
             } else if (CH == 1) {                // 1 component of 16 bits: a word is two pixels
                 const uint32_t a = now.t[(x >> 1) % NWD], b = now.b[(x >> 1) % NWD];
                 C[x][0] = (x & 1) ? smp(half_magic<1>(a), half_magic<1>(b)) : smp(half_magic<0>(a), half_magic<0>(b));
@@ -128,6 +133,8 @@ __global__ void __launch_bounds__(32, 16) plane_scale2_kernel(const __grid_const
                     }
                 }
             if (BP == 1) stg32(pd, pack4_u8(o[0][0], o[1][0], o[2][0], o[3][0]));
+            else if (SBITS == 8 && CH == 4) stg128(pd, make_uint4(pack4_u8(o[0][0], o[0][1 % CH], o[0][2 % CH], o[0][3 % CH]), pack4_u8(o[1][0], o[1][1 % CH], o[1][2 % CH], o[1][3 % CH]),
+                                                                  pack4_u8(o[2][0], o[2][1 % CH], o[2][2 % CH], o[2][3 % CH]), pack4_u8(o[3][0], o[3][1 % CH], o[3][2 % CH], o[3][3 % CH])));
             else if (SBITS == 8) stg64(pd, make_uint2(pack4_u8(o[0][0], o[0][CH - 1], o[1][0], o[1][CH - 1]), pack4_u8(o[2][0], o[2][CH - 1], o[3][0], o[3][CH - 1])));
             else if (CH == 1) stg64(pd, make_uint2(pack2_u16(o[0][0], o[1][0]), pack2_u16(o[2][0], o[3][0])));
             else stg128(pd, make_uint4(pack2_u16(o[0][0], o[0][CH - 1]), pack2_u16(o[1][0], o[1][CH - 1]), pack2_u16(o[2][0], o[2][CH - 1]), pack2_u16(o[3][0], o[3][CH - 1])));

@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(32, MINB) fused_csc_scale_stream_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The same machine for ONE PLANE of 8- or 16-bit samples with CH = 1 or 2 interleaved components (the Y and UV planes of
-// nv12 / yuv420p / p010 / p016 -> same format scaling: what the scale_cuda filter and the yuv -> yuv branch of sws_scale
+// The same machine for ONE PLANE of 8- or 16-bit samples with CH = 1 or 2 interleaved components, or 4 of 8 bits (the Y and
+// UV planes of nv12 / yuv420p / p010 / p016 -> same format scaling, and rgb0 / bgr0 / rgba / bgra -> same format: what the scale_cuda filter and the yuv -> yuv branch of sws_scale
 // do, swscale_cuda.c:372-476; any ratio, 2:1 included).  No colour conversion: a sample is RN(j / max) (R-B) or j (R-A).
 // A lane owns 8 pixels of both rows of a pair; outputs leave through a small shared-memory row so that the warp
 // stores whole words.
@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 if (!RA && P.wrap) o[c] = max(o[c], 0) & SMAX;      // GMATB_SWS_PARITY_WRAP (tests)
             }
             const int oi = out_index(i);
-            if (SBITS == 8) {
+            if (SBITS == 8 && CH == 4) {
+                reinterpret_cast<uint32_t *>(orow)[oi] = pack4_u8(o[0], o[1 % CH], o[2 % CH], o[3 % CH]);      // saturating
+            } else if (SBITS == 8) {
                 const uint32_t pw = pack4_u8(o[0], o[CH - 1], 0, 0);      // saturating
                 if (CH == 1) orow[oi] = (uint8_t)pw;
                 else reinterpret_cast<unsigned short *>(orow)[oi] = (unsigned short)pw;
@@ -438,6 +440,12 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 const uint32_t a = wt[j >> 1], b = wb[j >> 1];
                 if (j & 1) { S[0][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][0] = sample2(byte_magic<3>(a), byte_magic<3>(b)); }
                 else       { S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[1][0] = sample2(byte_magic<1>(a), byte_magic<1>(b)); }
+            } else if (SBITS == 8 && CH == 4) {        // two words: the 4 components of pixel 2j, of pixel 2j+1
+                const uint32_t a0 = wt[(2 * j) % NW], b0 = wb[(2 * j) % NW], a1 = wt[(2 * j + 1) % NW], b1 = wb[(2 * j + 1) % NW];
+                S[0][0] = sample2(byte_magic<0>(a0), byte_magic<0>(b0)); S[0][1 % CH] = sample2(byte_magic<1>(a0), byte_magic<1>(b0));
+                S[0][2 % CH] = sample2(byte_magic<2>(a0), byte_magic<2>(b0)); S[0][3 % CH] = sample2(byte_magic<3>(a0), byte_magic<3>(b0));
+                S[1][0] = sample2(byte_magic<0>(a1), byte_magic<0>(b1)); S[1][1 % CH] = sample2(byte_magic<1>(a1), byte_magic<1>(b1));
+                S[1][2 % CH] = sample2(byte_magic<2>(a1), byte_magic<2>(b1)); S[1][3 % CH] = sample2(byte_magic<3>(a1), byte_magic<3>(b1));
             } else if (SBITS == 8) {                   // one word: c0 c1 of pixel 2j, c0 c1 of pixel 2j+1
                 const uint32_t a = wt[j], b = wb[j];
                 S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[0][CH - 1] = sample2(byte_magic<1>(a), byte_magic<1>(b));

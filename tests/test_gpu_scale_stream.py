@@ -70,3 +70,15 @@ def test_plane_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh)
         _, _, b = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
         if not torch.equal(a.buf, b.buf):
             assert_same(a, b, f"plane stream vs tile kernel {name}{param} {fmt} {sw}x{sh}->{dw}x{dh}")
+
+
+# ---- 4-component packed rgb (rgb0 / bgra ...) -> same format: the scale_cuda filter on rgb frames -------------------------
+@pytest.mark.parametrize("name,flag,param", ALGOS)
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1920, 1080, 960, 540), (640, 360, 1280, 720), (64, 48, 40, 30), (33, 17, 50, 29),
+                                         (64, 48, 32, 24), (16, 4, 8, 2), (480, 12, 240, 6), (496, 12, 248, 6), (100, 60, 12, 7), (250, 34, 1000, 35), (18, 2, 7, 3)])
+def test_rgb4_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):
+    for fmt, wrap in ((FMT.RGB0, SWS.PARITY_WRAP), (FMT.BGRA, 0)):
+        _, _, a = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, seed=sw + dh)
+        _, _, b = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
+        if not torch.equal(a.buf, b.buf):
+            assert_same(a, b, f"rgb4 stream vs tile kernel {name}{param} {fmt} {sw}x{sh}->{dw}x{dh}")
