@@ -556,8 +556,8 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     if (!si.pl[0].p || !di.pl[0].p) return GMATB_ERR_INVAL;
     // exactly 2:1, R-B: the register-streaming plane kernel (scale_plane2.cuh)
     // (its taps are at 2 o - 1 .. 2 o + 2 on both axes: true of bicubic / Lanczos / bilinear at 2:1, not of nearest)
-    const bool plane_ok = ch == 1 || ch == 2 || (ch == 4 && bits == 8);
-    if (plane_ok && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->algo != RS_NEAREST && c->hpx[bank][0] == -1 && c->hpy[bank][0] == -1 && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
+    const bool plane_ok = ch == 1 || ch == 2 || ((ch == 3 || ch == 4) && bits == 8);
+    if (plane_ok && ch != 3 && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->algo != RS_NEAREST && c->hpx[bank][0] == -1 && c->hpy[bank][0] == -1 && pw == 2 * dw && ph == 2 * dh && (pw % 8) == 0 &&
         planes_aligned(si, 1, ch * bits == 8 ? 8 : 16) && planes_aligned(di, 1, std::min(16, 4 * ch * bits / 8))) {
         if (!c->pw2_state[bank]) {
             float4 hx, hy;
@@ -592,7 +592,7 @@ static int plane_resample(GmatbSws *c, int bank, const GmatbImage *s, const Gmat
     // 8- and 16-bit planes of 1 or 2 components: the streaming kernel (scale_stream.cuh)
     const int bp = ch * bits / 8;
     if (plane_ok && !(c->flags & GMATB_SWS_TILE_KERNEL) && c->splan_state[bank] >= 0 &&
-        planes_aligned(si, 1, bp == 1 ? 8 : 16) && planes_aligned(di, 1, 4) && si.pl[0].pitch >= ((pw + 7) & ~7) * bp) {
+        planes_aligned(si, 1, (bp == 1 || bp == 3) ? 8 : 16) && planes_aligned(di, 1, 4) && si.pl[0].pitch >= ((pw + 7) & ~7) * bp) {
         if (c->splan_state[bank] == 0) c->splan_state[bank] = build_stream_plan(c, bank, pw, ph, dw) ? 1 : -1;
         if (c->splan_state[bank] == 1) {
             PlaneStreamParams P;

@@ -38,13 +38,13 @@ int stream_launch(bool semi, int dc, int nout, int deal, int ra, dim3 g, cudaStr
 
 template <int CH, int SBITS>
 static void launch_plane_t(int nout, int deal, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P) {
-#define PK(N_, D_, R_) plane_scale_stream_kernel<CH, SBITS, N_, D_, R_, (CH == 4 ? 12 : 16)><<<g, 32, 0, st>>>(P)
+#define PK(N_, D_, R_) plane_scale_stream_kernel<CH, SBITS, N_, D_, R_, (CH >= 3 ? 12 : 16)><<<g, 32, 0, st>>>(P)
     if (ra) { if (nout <= 3) PK(3, 0, 1); else if (deal) PK(5, 1, 1); else PK(5, 0, 1); }
     else    { if (nout <= 3) PK(3, 0, 0); else if (deal) PK(5, 1, 0); else PK(5, 0, 0); }
 #undef PK
 }
 int plane_stream_launch(int ch, int bits, int nout, int deal, int ra, dim3 g, cudaStream_t st, const PlaneStreamParams &P) {
-    if (bits == 8) { if (ch == 1) launch_plane_t<1, 8>(nout, deal, ra, g, st, P); else if (ch == 2) launch_plane_t<2, 8>(nout, deal, ra, g, st, P); else launch_plane_t<4, 8>(nout, deal, ra, g, st, P); }
+    if (bits == 8) { if (ch == 1) launch_plane_t<1, 8>(nout, deal, ra, g, st, P); else if (ch == 2) launch_plane_t<2, 8>(nout, deal, ra, g, st, P); else if (ch == 3) launch_plane_t<3, 8>(nout, deal, ra, g, st, P); else launch_plane_t<4, 8>(nout, deal, ra, g, st, P); }
     else           { if (ch == 1) launch_plane_t<1, 16>(nout, deal, ra, g, st, P); else launch_plane_t<2, 16>(nout, deal, ra, g, st, P); }
     count_launch();
     return set_cuda_error(cudaGetLastError());

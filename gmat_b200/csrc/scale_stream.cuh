@@ -331,7 +331,10 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
     struct Rows { uint32_t t[NW], b[NW]; };
     auto load_row = [&](const uint8_t *q, uint32_t (&w)[NW]) {
         if (NW == 2) { const uint2 a = ldg64(q); w[0] = a.x; w[1] = a.y; }
-        else {
+        else if (NW == 6) {                            // 3 components of 8 bits: 24 bytes, 8-byte aligned
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const uint2 a = ldg64(q + 8 * k); w[(2 * k) % NW] = a.x; w[(2 * k + 1) % NW] = a.y; }
+        } else {
 #pragma unroll
             for (int k = 0; k < NW / 4; k++) {
                 const uint4 a = ldg128(q + 16 * k);
@@ -372,7 +375,10 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 if (!RA && P.wrap) o[c] = max(o[c], 0) & SMAX;      // GMATB_SWS_PARITY_WRAP (tests)
             }
             const int oi = out_index(i);
-            if (SBITS == 8 && CH == 4) {
+            if (SBITS == 8 && CH == 3) {
+                const uint32_t pw = pack4_u8(o[0], o[1 % CH], o[2 % CH], 0);      // saturating
+                orow[3 * oi] = (uint8_t)pw; orow[3 * oi + 1] = (uint8_t)(pw >> 8); orow[3 * oi + 2] = (uint8_t)(pw >> 16);
+            } else if (SBITS == 8 && CH == 4) {
                 reinterpret_cast<uint32_t *>(orow)[oi] = pack4_u8(o[0], o[1 % CH], o[2 % CH], o[3 % CH]);      // saturating
             } else if (SBITS == 8) {
                 const uint32_t pw = pack4_u8(o[0], o[CH - 1], 0, 0);      // saturating
@@ -419,6 +425,12 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
             const int bits = 16 * rot;
             const uint32_t lo = (bits & 32) ? w[1] : w[0], hi = (bits & 32) ? w[0] : w[1];
             w[0] = __funnelshift_r(lo, hi, bits & 31); w[1] = __funnelshift_r(hi, lo, bits & 31);
+        } else if (NW == 6) {                          // a pair is 6 bytes: by 3 words (two pairs), then by 1 word + 16 bits (one pair)
+            uint32_t a[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) a[k] = (rot & 2) ? w[(k + 3) % NW] : w[k];
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = (rot & 1) ? __funnelshift_r(a[(k + 1) % NW], a[(k + 2) % NW], 16) : a[k];
         } else {                                       // a pair is NW / 4 whole words: two conditional stages
             uint32_t a[NW];
 #pragma unroll
@@ -440,6 +452,16 @@ __global__ void __launch_bounds__(32, MINB) plane_scale_stream_kernel(const __gr
                 const uint32_t a = wt[j >> 1], b = wb[j >> 1];
                 if (j & 1) { S[0][0] = sample2(byte_magic<2>(a), byte_magic<2>(b)); S[1][0] = sample2(byte_magic<3>(a), byte_magic<3>(b)); }
                 else       { S[0][0] = sample2(byte_magic<0>(a), byte_magic<0>(b)); S[1][0] = sample2(byte_magic<1>(a), byte_magic<1>(b)); }
+            } else if (SBITS == 8 && CH == 3) {        // bytes 6j .. 6j+5: component c of pixel 2j+h is byte 6j + 3h + c
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const int B = 6 * j + 3 * h + c;
+                        const uint32_t a = wt[(B >> 2) % NW], b = wb[(B >> 2) % NW];
+                        S[h][c % CH] = (B & 3) == 0 ? sample2(byte_magic<0>(a), byte_magic<0>(b)) : (B & 3) == 1 ? sample2(byte_magic<1>(a), byte_magic<1>(b))
+                                     : (B & 3) == 2 ? sample2(byte_magic<2>(a), byte_magic<2>(b)) : sample2(byte_magic<3>(a), byte_magic<3>(b));
+                    }
             } else if (SBITS == 8 && CH == 4) {        // two words: the 4 components of pixel 2j, of pixel 2j+1
                 const uint32_t a0 = wt[(2 * j) % NW], b0 = wb[(2 * j) % NW], a1 = wt[(2 * j + 1) % NW], b1 = wb[(2 * j + 1) % NW];
                 S[0][0] = sample2(byte_magic<0>(a0), byte_magic<0>(b0)); S[0][1 % CH] = sample2(byte_magic<1>(a0), byte_magic<1>(b0));

@@ -77,8 +77,19 @@ def test_plane_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh)
 @pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1920, 1080, 960, 540), (640, 360, 1280, 720), (64, 48, 40, 30), (33, 17, 50, 29),
                                          (64, 48, 32, 24), (16, 4, 8, 2), (480, 12, 240, 6), (496, 12, 248, 6), (100, 60, 12, 7), (250, 34, 1000, 35), (18, 2, 7, 3)])
 def test_rgb4_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):
-    for fmt, wrap in ((FMT.RGB0, SWS.PARITY_WRAP), (FMT.BGRA, 0)):
+    for fmt, wrap in ((FMT.RGB0, SWS.PARITY_WRAP), (FMT.BGRA, 0), (FMT.RGB24, 0), (FMT.BGR24, SWS.PARITY_WRAP)):
         _, _, a = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, seed=sw + dh)
         _, _, b = run(dev, fmt, fmt, sw, sh, dw, dh, flag | wrap, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
         if not torch.equal(a.buf, b.buf):
-            assert_same(a, b, f"rgb4 stream vs tile kernel {name}{param} {fmt} {sw}x{sh}->{dw}x{dh}")
+            assert_same(a, b, f"rgb stream vs tile kernel {name}{param} {fmt} {sw}x{sh}->{dw}x{dh}")
+
+
+@pytest.mark.parametrize("name,flag,param", [("bicubic", SWS.BICUBIC, (0.75,)), ("bilinear", SWS.BILINEAR, None)])
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1920, 1080, 960, 540), (640, 360, 1280, 720), (64, 48, 40, 30), (250, 34, 1000, 36)])
+def test_rgb_to_yuv_prescale_stream_equals_tile_kernel(dev, name, flag, param, sw, sh, dw, dh):
+    """rgb -> yuv with scaling = resize the rgb image, then convert (swscale_cuda.c:312-341): the resize through the plane kernels"""
+    for sfmt, dfmt in ((FMT.RGB24, FMT.NV12), (FMT.BGRA, FMT.YUV420P)):
+        _, _, a = run(dev, sfmt, dfmt, sw, sh, dw, dh, flag, param, seed=sw + dh)
+        _, _, b = run(dev, sfmt, dfmt, sw, sh, dw, dh, flag, param, extra=SWS.TILE_KERNEL, seed=sw + dh)
+        if not torch.equal(a.buf, b.buf):
+            assert_same(a, b, f"rgb->yuv prescale stream vs tile {name}{param} {sfmt}->{dfmt} {sw}x{sh}->{dw}x{dh}")

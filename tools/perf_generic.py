@@ -47,3 +47,11 @@ for (sw, sh, dw, dh, B) in ((3840, 2160, 1920, 1080, 16), (1920, 1080, 1280, 720
         c = SwsContext(sw, sh, FMT.RGB0, dw, dh, FMT.RGB0, SWS.BICUBIC | SWS.HWACCEL_CUDA | extra)
         ms = timeit(lambda: c.scale(src, dst))
         print(f"rgb0->rgb0 {sw}x{sh}->{dw}x{dh} bicubic   {kname:6s}: {ms:.3f} ms {B*sw*sh/ms/1e6:7.1f} Gpx/s(src) {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/PEAK*100:5.1f}%", flush=True)
+for (sw, sh, dw, dh, B) in ((1920, 1080, 1280, 720, 32), (3840, 2160, 1280, 720, 16)):
+    src = FrameBatch(FMT.RGB24, sw, sh, B, device=dev); src.buf.random_(0, 256)
+    dst = FrameBatch(FMT.RGB24, dw, dh, B, device=dev)
+    alg = B * (sw * sh * 3.0 + dw * dh * 3.0)
+    for kname, extra in (("stream", 0), ("tile", SWS.TILE_KERNEL)):
+        c = SwsContext(sw, sh, FMT.RGB24, dw, dh, FMT.RGB24, SWS.BICUBIC | SWS.HWACCEL_CUDA | extra)
+        ms = timeit(lambda: c.scale(src, dst))
+        print(f"rgb24->rgb24 {sw}x{sh}->{dw}x{dh} bicubic   {kname:6s}: {ms:.3f} ms {B*sw*sh/ms/1e6:7.1f} Gpx/s(src) {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/PEAK*100:5.1f}%", flush=True)
