@@ -281,6 +281,7 @@ __host__ __device__ inline int border_idx(int i, int n, int mode) {
 }  // namespace gmatb
 #include "gauss_stream.cuh"
 #include "median3_stream.cuh"
+#include "median5_stream.cuh"
 #include "rotate_linear.cuh"
 namespace gmatb {
 
@@ -631,6 +632,26 @@ extern "C" int gmatb_median(const GmatbImage *src, const GmatbImage *dst, int kw
         else            median3_stream_kernel<4><<<g3, 128, 0, (cudaStream_t)stream>>>(P);
         count_launch();
         return set_cuda_error(cudaGetLastError());
+    }
+    if (kw == 5 && kh == 5 && al16(s) && al16(d) && d.h >= 1) {
+        // streaming u16x2 kernel (median5_stream.cuh): a thread owns NOUT pixels of two row bands
+        // 8 pixels per thread when the row allows (halo columns 12 / 8 instead of 8 / 4), else 4
+        const int nout = wbytes % (8 * d.bpp) == 0 ? 8 : wbytes % (4 * d.bpp) == 0 ? 4 : 0;
+        if (nout) {
+            Med3Params P;
+            P.sp = s.p; P.dp = d.p; P.spitch = s.pitch; P.dpitch = d.pitch; P.sbs = s.bstride; P.dbs = d.bstride;
+            P.wb = wbytes; P.H = d.h;
+            const int S = nout * d.bpp, nbt = nbatch(src), gx = (wbytes / S + 127) / 128;
+            int rows = 32;
+            while (rows > 4 && (long long)gx * ((d.h + 2 * rows - 1) / (2 * rows)) * nbt < 148LL * 2 * 4) rows >>= 1;
+            P.rows = rows;
+            dim3 g5(gx, (d.h + 2 * rows - 1) / (2 * rows), nbt);
+            cudaStream_t st = (cudaStream_t)stream;
+            if (nout == 8) { if (d.bpp == 3) median5_stream_kernel<3, 8><<<g5, 128, 0, st>>>(P); else median5_stream_kernel<4, 8><<<g5, 128, 0, st>>>(P); }
+            else           { if (d.bpp == 3) median5_stream_kernel<3, 4><<<g5, 128, 0, st>>>(P); else median5_stream_kernel<4, 4><<<g5, 128, 0, st>>>(P); }
+            count_launch();
+            return set_cuda_error(cudaGetLastError());
+        }
     }
     if ((kw == 3 && kh == 3) || (kw == 5 && kh == 5)) {
         const size_t sm2 = (size_t)(64 + kw - 1) * (8 + kh - 1) * d.bpp;

@@ -120,6 +120,32 @@ def test_median3_stream_kernel(dev, fmt, w, h, n):
     assert_same(dd, ref, f"median3 stream {w}x{h}x{n}")
 
 
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("w,h,n", [(8, 5, 1), (16, 5, 1), (24, 9, 2), (40, 17, 3), (48, 6, 1), (256, 67, 2), (1920, 1080, 2), (3840, 130, 1), (36, 21, 1)])
+def test_median5_stream_kernel(dev, fmt, w, h, n):
+    """the streaming 5x5 kernel (W % 8 == 0: 8 pixels per thread, else W % 4 == 0: 4): one-thread rows (both frame edges in
+    one strip), band seams, heights below the window, batches; (36, 21) takes the 4-pixel instantiation"""
+    src, ds = pair(fmt, w, h, dev, n)
+    dd = FrameBatch(fmt, w, h, n, device=dev); g.median(ds, dd, 5, 5); torch.cuda.synchronize()
+    ref = FrameBatch(fmt, w, h, n); s, d = src.image(), ref.image()
+    orc.orc().orc_median(C.byref(s), C.byref(d), 5, 5)
+    assert_same(dd, ref, f"median5 stream {w}x{h}x{n}")
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_median5_stream_kernel_low_entropy(dev, fmt):
+    """ties everywhere: 2-level and 4-level content (the min/max blocks must not depend on distinct samples)"""
+    w, h = 64, 40
+    for levels in (2, 4):
+        src = FrameBatch(fmt, w, h, 2)
+        src.buf[:] = np.random.default_rng(levels).integers(0, levels, src.buf.size, dtype=np.uint8) * np.uint8(255 // (levels - 1))
+        ds = src.to(dev)
+        dd = FrameBatch(fmt, w, h, 2, device=dev); g.median(ds, dd, 5, 5); torch.cuda.synchronize()
+        ref = FrameBatch(fmt, w, h, 2); s, d = src.image(), ref.image()
+        orc.orc().orc_median(C.byref(s), C.byref(d), 5, 5)
+        assert_same(dd, ref, f"median5 stream levels={levels}")
+
+
 def test_constant_image_is_a_fixed_point(dev):
     w, h = 1920, 1080
     src = FrameBatch(FMT.RGB24, w, h, 1, device=dev); src.buf.fill_(0)
