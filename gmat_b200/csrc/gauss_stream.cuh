@@ -30,7 +30,13 @@ __device__ __noinline__ int border_row(int y, int H, int mode) { return border_i
 // PF2: loads are issued two rows ahead of their use (three row buffers) instead of one.  Measured on B200, 4K, 5x5:
 // rgb24 (96 registers, 5 CTAs/SM) 433 Gpx/s with one row ahead, 397 with two (126 registers, 4 CTAs/SM);
 // rgba 289 -> 341 Gpx/s: the 4-byte pixel form is the latency-bound one.
-template <int BPP, int KW, int KH, bool INTERIOR, bool PF2>
+// RING > 0: the rows are fetched RING - 1 steps ahead by 4-byte cp.async copies into a per-thread column of a shared-memory
+// ring (slot-major, [slot][word][thread]: conflict-free, and a thread only ever reads what it copied itself, so
+// cp.async.wait_group is the only synchronisation: no barrier, no mbarrier) and picked up by LDS when their step
+// comes.  The register forms above can keep one or two rows in flight (one step is ~150 instructions; 4-5 resident
+// warps per scheduler cover ~750 issue cycles, about one loaded-DRAM latency: ncu long-scoreboard 3.2 per issue);
+// the ring keeps RING - 1 rows in flight at no register cost.
+template <int BPP, int KW, int KH, bool INTERIOR, bool PF2, int RING = 0>
 __device__ __forceinline__ void gauss_stream_band(const uint8_t *sp, int spitch, long long sbs,
                                                   uint8_t *dp, int dpitch, long long dbs, int H, int t0, int t1, const GaussS &G) {
     constexpr int RX = KW / 2, RY = KH / 2, NPX = 4;
@@ -55,6 +61,36 @@ __device__ __forceinline__ void gauss_stream_band(const uint8_t *sp, int spitch,
 
     const int nrows = (y_end - y_begin) + KH - 1;
     uint32_t w[NWORDS], wn[NWORDS], wnn[NWORDS];   // rows i, i+1, i+2: loads are issued two steps ahead of their use
+    extern __shared__ uint32_t gs_ring[];
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(gs_ring) + threadIdx.x * 4u;
+    // RING: copy row i into slot i % RING (one commit group per call, also when nothing is copied)
+    auto fetch_ring = [&](int i) {
+        int sy = y_begin - RY + i;
+        const uint32_t sa = ring0 + (uint32_t)((i % (RING > 0 ? RING : 1)) * NWORDS) * 512u;
+        bool zero = false;
+        if (!INTERIOR) {
+            if ((unsigned)sy >= (unsigned)H) sy = border_row(sy, H, G.border);
+            zero = sy < 0;
+        } else sy = min(sy, H - 1);
+        if (i < nrows) {
+            if (zero) {
+#pragma unroll
+                for (int k = 0; k < NWORDS; k++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + k * 512u), "r"(0u) : "memory");
+            } else {
+                const uint8_t *q = ps + (size_t)sy * spitch;
+#pragma unroll
+                for (int k = 0; k < NWORDS; k++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + k * 512u), "l"(q + 4 * k) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto take_ring = [&](int i, uint32_t (&dst)[NWORDS]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING > 1 ? RING - 2 : 0) : "memory");
+        const uint32_t sa = ring0 + (uint32_t)((i % (RING > 0 ? RING : 1)) * NWORDS) * 512u;
+#pragma unroll
+        for (int k = 0; k < NWORDS; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dst[k]) : "r"(sa + k * 512u) : "memory");
+    };
     auto fetch = [&](int i, uint32_t (&dst)[NWORDS]) {
         int sy = y_begin - RY + i;
         if (INTERIOR) {
@@ -76,14 +112,20 @@ __device__ __forceinline__ void gauss_stream_band(const uint8_t *sp, int spitch,
             for (int k = 0; k < NWORDS; k++) dst[k] = __ldg(q + k);
         }
     };
-    fetch(0, w);
-    if (PF2) fetch(1, wn);
+    if (RING > 0) {
+#pragma unroll 1
+        for (int i = 0; i < RING - 1; i++) fetch_ring(i);
+    } else {
+        fetch(0, w);
+        if (PF2) fetch(1, wn);
+    }
     for (int i0 = 0; i0 < nrows; i0 += KH) {
 #pragma unroll
         for (int ph = 0; ph < KH; ph++) {
             const int i = i0 + ph;
             if (i >= nrows) break;
-            if (PF2) fetch(i + 2, wnn); else fetch(i + 1, wn);
+            if (RING > 0) { take_ring(i, w); fetch_ring(i + RING - 1); }   // into the slot read one step ago
+            else if (PF2) fetch(i + 2, wnn); else fetch(i + 1, wn);
             // ---- window of this row as floats: even-aligned pairs E, odd-aligned pairs O (BPP 3 needs both) ----
             f2 E[(NWIN + 1) / 2], O[(NWIN + 1) / 2];
             {
@@ -143,10 +185,25 @@ __device__ __forceinline__ void gauss_stream_band(const uint8_t *sp, int spitch,
                     q[wv] = word;
                 }
             }
+            if (RING == 0) {
 #pragma unroll
-            for (int k = 0; k < NWORDS; k++) { w[k] = wn[k]; if (PF2) wn[k] = wnn[k]; }
+                for (int k = 0; k < NWORDS; k++) { w[k] = wn[k]; if (PF2) wn[k] = wnn[k]; }
+            }
         }
     }
+}
+
+// words of one ring slot per thread: the host sizes the dynamic shared memory with it
+constexpr int gauss_ring_words(int bpp, int kw) {
+    return ((4 - ((kw / 2 * bpp) & 3)) & 3) + (4 + kw - 1) * bpp + 3 >> 2;
+}
+
+template <int BPP, int KW, int KH, int RING>
+__global__ void __launch_bounds__(128, BPP == 4 ? 4 : 5) gauss_ring_kernel(const uint8_t *sp, int spitch, long long sbs,
+                                                             uint8_t *dp, int dpitch, long long dbs, int H, int t0, int t1, GaussS G) {
+    const int y_begin = blockIdx.y * G.band, y_end = min(y_begin + G.band, H);
+    if (y_begin - KH / 2 >= 0 && y_end + KH / 2 <= H) gauss_stream_band<BPP, KW, KH, true, false, RING>(sp, spitch, sbs, dp, dpitch, dbs, H, t0, t1, G);
+    else                                             gauss_stream_band<BPP, KW, KH, false, false, RING>(sp, spitch, sbs, dp, dpitch, dbs, H, t0, t1, G);
 }
 
 template <int BPP, int KW, int KH, int MINB>

@@ -38,6 +38,8 @@ if "gauss" in which:
     g.gaussian(a, b, 5, 5, 1.1, 1.1, BORDER.REFLECT101)
 if "median" in which:
     g.median(a, b, 3, 3)
+if "median5" in which:
+    g.median(a, b, 5, 5)
 if "rgb2yuv" in which:
     back = FrameBatch(FMT.NV12, 3840, 2160, B, device=dev); g.rgb2yuv(a, back)
 if "fliph" in which:
