@@ -111,7 +111,7 @@ static __global__ void filter_table_kernel(int algo, int src_n, int dst_n, float
 // wrong for about half of all j.  The saturation implements both clamps (j < 0 -> 0,
 // j > max -> 1).  The generic kernel keeps the older two-term form sat(FFMA(j, khi,
 // RN(j*klo))), khi + klo = 1/max to 48 bits (same exhaustive check).
-struct NormK { float khi, klo, c1, c0, c2; };
+struct NormK { float khi, klo, c1, c0, c2; float kd; int jmax; };
 
 __device__ __forceinline__ f2 add2_rz(f2 a, f2 b) {
     f2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
@@ -127,5 +127,27 @@ __device__ __forceinline__ f2 quant_norm2(f2 r, const NormK &k) {
     upk(hi, h0, h1);
     return pk(fma_sat(h0, k.c2, h0), fma_sat(h1, k.c2, h1));
 }
+
+// The same sample, scaled by 2^-NORM_SHIFT (14 for 8-bit, 6 for 16-bit sources), with every FP32 operation PACKED and the clamp
+// on the integer pipe in ONE instruction (the headline kernel's form, scale_fused3.cuh):
+//   d  = FMUL2.RZ(r, 2^-149)         bit pattern = trunc(r), sign-magnitude: as s32, negative for r < 0
+//   j  = VIMNMX.RELU(d, max)         = max(min(d, max), 0): both clamps; still the denormal float j * 2^-149
+//   hi = FMUL2(j, kd)                kd = c1 * 2^(149 - NORM_SHIFT): j*c1 * 2^-NORM_SHIFT EXACTLY (j*0x010101 < 2^24)
+//   p' = FFMA2(hi, c2, hi)           = RN(j/max) * 2^-NORM_SHIFT: scaling by a power of two commutes with the rounding
+// The horizontal and vertical chains are linear in the samples with constant weights, so every intermediate is the
+// reference's value times 2^-NORM_SHIFT exactly (no underflow: the host refuses weights below 2^-40), and the final
+// multiply uses factor * 2^NORM_SHIFT.  Why: FFMA.SAT exists only as a scalar instruction, and a stream that alternates
+// scalar and packed FP32 instructions retires ~81-89 % of the lane-operations of a homogeneous one
+// (profiles/r1c_probe2_operand_forms.txt: "alt 4 FFMA2 + 4 FFMA" 3.24 units/clk/SM vs 4.0) -- the 19 % the fma pipe of
+// the round-1 kernel was idle while throttling.
+__device__ __forceinline__ f2 quant_norm2d(f2 r, const NormK &k) {
+    int j0, j1;
+    upki(mul2_rz(r, bc(GMATB_TWO_M149)), j0, j1);
+    j0 = __vimin_s32_relu(j0, k.jmax); j1 = __vimin_s32_relu(j1, k.jmax);
+    f2 jj; asm("mov.b64 %0, {%1, %2};" : "=l"(jj) : "r"(j0), "r"(j1));
+    const f2 hi = mul2(jj, bc(k.kd));
+    return fma2(hi, bc(k.c2), hi);
+}
+constexpr int norm_shift(int bits) { return bits == 8 ? 14 : 6; }
 
 }  // namespace gmatb

@@ -236,6 +236,9 @@ static NormK norm_k(int bits) {
     k.c1 = bits == 8 ? 65793.0f / 16777216.0f : 1.0f / 65536.0f;
     k.c0 = -8388608.0f * k.c1;
     k.c2 = bits == 8 ? 1.0f / 16777216.0f : 1.0f / 65536.0f + 1.0f / 4294967296.0f;
+    // denormal-domain form (quant_norm2d): c1 * 2^(149 - shift) = 0x010101 * 2^111 (8 bit), 2^127 (16 bit)
+    k.kd = ldexpf(bits == 8 ? 65793.0f : 1.0f, bits == 8 ? 111 : 127);
+    k.jmax = bits == 8 ? 255 : 65535;
     return k;
 }
 
@@ -334,6 +337,12 @@ static int run_fused(GmatbSws *c, const GmatbImage *src, const GmatbImage *dst, 
     P.nk = norm_k(bits);
     P.factor = bits == 8 ? 255.f : 65535.f;
     P.factor_q = P.factor * 0.25f;
+    // yuv sources carry their samples scaled by 2^-norm_shift through the chains (quant_norm2d); weights so small that a
+    // scaled product could leave the normal range do not occur in any filter table, but are refused all the same
+    P.factor_s = ldexpf(P.factor, norm_shift(bits)); P.factor_qs = ldexpf(P.factor_q, norm_shift(bits));
+    for (int i = 0; i < 4; i++) {
+        if ((c->wx[i] != 0.f && fabsf(c->wx[i]) < 9.094947e-13f) || (c->wy[i] != 0.f && fabsf(c->wy[i]) < 9.094947e-13f)) return 0;
+    }
     P.dstW = c->dstW; P.dstH = c->dstH;
     const int batch = src->batch > 1 ? src->batch : 1;
     // 4-tap: strips overlap by one lane per side (30 owning lanes per warp); 2-tap: 32

@@ -37,6 +37,7 @@ struct alignas(8) Fused3Params {
     NormK nk;
     float factor;      // 255 or 65535
     float factor_q;    // factor / 4 (exact), TAPS2
+    float factor_s, factor_qs;   // the same times 2^norm_shift: yuv sources run the chains on scaled samples (quant_norm2d)
     int band;
     int dstW, dstH;
 };
@@ -119,7 +120,7 @@ __device__ __forceinline__ void produce3(const Raw3<L, SBITS> &R, const Fused3Pa
                 f2 xb = fma2(fy2, bc(P.m6), bc(t1b));
                 if (FMAFORM) { xr = fma2(bc(fv), bc(P.cm72[1]), xr); xg = fma2(bc(fv), bc(P.cm45[1]), xg); }
                 else { xr = add2(xr, bc(t2r)); xg = add2(xg, bc(t2g)); }
-                C[col][0] = quant_norm2(xr, P.nk); C[col][1] = quant_norm2(xg, P.nk); C[col][2] = quant_norm2(xb, P.nk);
+                C[col][0] = quant_norm2d(xr, P.nk); C[col][1] = quant_norm2d(xg, P.nk); C[col][2] = quant_norm2d(xb, P.nk);
             }
         }
     }
@@ -134,7 +135,7 @@ struct Fused3 {
     // loads of the row pair two steps ahead into the same buffer as soon as its raw words are consumed
     // (measured DRAM latency under load is ~2 steps of a warp's instruction stream at 4 warps/SMSP).
     template <typename Refill>
-    static __device__ __forceinline__ void step(const Fused3Params &P, Row &cur, float (&acc)[4][3], float (&hb_prev)[4][3],
+    static __device__ __forceinline__ void step(const Fused3Params &P, Row &cur, f2 (&acc)[2][3], f2 (&hb_prev)[2][3],
                                                 bool store, uint8_t *pd, int alpha_i, Refill refill) {
         f2 C[8][3];
         if (SBITS == 8) {
@@ -150,29 +151,48 @@ struct Fused3 {
 #pragma unroll
             for (int c = 0; c < 3; c++) { PL[c] = shfl_up2(C[7][c]); PR[c] = shfl_dn2(C[0][c]); }
         }
-        float ht[4][3], hbm[4][3];
+        // horizontal results of the row pair, re-paired for the vertical pass: HT / HB = the top / bottom row of two
+        // neighbouring output columns (two register moves per pair: the vertical chain, the factor multiply and the
+        // truncation then run packed like everything before them -- a homogeneous FFMA2 stream, see quant_norm2d)
+        f2 HT[2][3], HB[2][3];
+        float s2[4][3];                       // TAPS2: top + bottom of each output column (no re-pairing: measured 1.7 % faster scalar)
 #pragma unroll
-        for (int xo = 0; xo < 4; xo++)
+        for (int xp = 0; xp < 2; xp++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const f2 p0 = xo == 0 ? PL[c] : C[2 * xo - 1][c];
-                const f2 p3 = xo == 3 ? PR[c] : C[2 * xo + 2][c];
-                // TAPS2: weights are exactly {0, .5, .5, 0}: FFMA(.5, p2, FMUL(.5, p1)) == RN(p1 + p2) / 2 (scaling by a
-                // power of two commutes with rounding), so the halvings are deferred to the final factor
-                const f2 h = TAPS2 ? add2(C[2 * xo][c], C[2 * xo + 1][c]) : hpass<false>(P.wx, p0, C[2 * xo][c], C[2 * xo + 1][c], p3);
-                upk(h, ht[xo][c], hbm[xo][c]);
+                float t0, b0, t1, b1;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int xo = 2 * xp + q;
+                    const f2 p0 = xo == 0 ? PL[c] : C[2 * xo - 1][c];
+                    const f2 p3 = xo == 3 ? PR[c] : C[2 * xo + 2][c];
+                    // TAPS2: weights are exactly {0, .5, .5, 0}: FFMA(.5, p2, FMUL(.5, p1)) == RN(p1 + p2) / 2 (scaling by a
+                    // power of two commutes with rounding), so the halvings are deferred to the final factor
+                    const f2 h = TAPS2 ? add2(C[2 * xo][c], C[2 * xo + 1][c]) : hpass<false>(P.wx, p0, C[2 * xo][c], C[2 * xo + 1][c], p3);
+                    if (q == 0) upk(h, t0, b0); else upk(h, t1, b1);
+                }
+                if (TAPS2) { s2[2 * xp][c] = __fadd_rn(b0, t0); s2[2 * xp + 1][c] = __fadd_rn(b1, t1); }
+                else { HT[xp][c] = pk(t0, t1); HB[xp][c] = pk(b0, b1); }
             }
         if (store) {
             int o[4][3];
+            const float fac = L == L_RGB3 ? (TAPS2 ? P.factor_q : P.factor) : (TAPS2 ? P.factor_qs : P.factor_s);
 #pragma unroll
-            for (int xo = 0; xo < 4; xo++)
+            for (int xp = 0; xp < 2; xp++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     // TAPS2: the output row taps only this pair: RN(2h_top + 2h_bottom) = 4 x the reference's vertical
                     // result, exactly, written in the same step (pd addresses row k)
-                    const float v = TAPS2 ? __fadd_rn(hbm[xo][c], ht[xo][c]) : __fmaf_rn(P.wy[3], ht[xo][c], acc[xo][c]);
-                    o[xo][c] = trunc_i(__fmul_rn(v, TAPS2 ? P.factor_q : P.factor));
-                    if (WRAP) o[xo][c] = max(o[xo][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
+                    if (TAPS2) {
+                        o[2 * xp][c] = trunc_i(__fmul_rn(s2[2 * xp][c], fac)); o[2 * xp + 1][c] = trunc_i(__fmul_rn(s2[2 * xp + 1][c], fac));
+                    } else {
+                        const f2 v = fma2(bc(P.wy[3]), HT[xp][c], acc[xp][c]);
+                        upki(mul2_rz(mul2(v, bc(fac)), bc(GMATB_TWO_M149)), o[2 * xp][c], o[2 * xp + 1][c]);
+                    }
+                    if (WRAP) {
+                        o[2 * xp][c] = max(o[2 * xp][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
+                        o[2 * xp + 1][c] = max(o[2 * xp + 1][c], 0) & (SBITS == 8 ? 0xFF : 0xFFFF);
+                    }
                 }
             constexpr bool SW = dst_swap(DST);
 #define CH(i, c) o[i][SW ? 2 - (c) : (c)]
@@ -196,15 +216,15 @@ struct Fused3 {
 #undef CH
         }
 #pragma unroll
-        for (int xo = 0; xo < 4; xo++)
+        for (int xp = 0; xp < 2; xp++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 if (TAPS2) continue;
-                float t = __fmul_rn(P.wy[1], ht[xo][c]);
-                t = __fmaf_rn(P.wy[0], hb_prev[xo][c], t);
-                t = __fmaf_rn(P.wy[2], hbm[xo][c], t);
-                acc[xo][c] = t;
-                hb_prev[xo][c] = hbm[xo][c];
+                f2 t = mul2(bc(P.wy[1]), HT[xp][c]);
+                t = fma2(bc(P.wy[0]), hb_prev[xp][c], t);
+                t = fma2(bc(P.wy[2]), HB[xp][c], t);
+                acc[xp][c] = t;
+                hb_prev[xp][c] = HB[xp][c];
             }
     }
 };
@@ -266,11 +286,11 @@ __device__ __forceinline__ void fused3_band(const Fused3Params &P, const int bx,
         load_at(R, rt * pitch_y, rb * pitch_y, rc * pitch_c, rc * pitch_c2);
     };
 
-    float hb_prev[4][3], acc[4][3];
+    f2 hb_prev[2][3], acc[2][3];          // vertical state of the 4 output columns, two columns per register pair
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) { hb_prev[i][c] = 0.f; acc[i][c] = 0.f; }
+        for (int c = 0; c < 3; c++) { hb_prev[i][c] = 0ull; acc[i][c] = 0ull; }
 
     // constant alpha of 4-channel outputs: the chain applied to a constant 1.0 image
     int alpha_i = 0;
