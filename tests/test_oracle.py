@@ -92,6 +92,51 @@ def test_norm_geometric_form_is_exact():
         assert np.array_equal(p, ref)
 
 
+def test_norm_denormal_domain_form_is_exact_and_scaled():
+    """quant_norm2d (resample_core.cuh), the all-packed form of the headline kernel: j read as the denormal float j*2^-149,
+    hi' = j*kd exactly (kd = c1*2^(149-shift)), p' = FFMA(hi', c2, hi') == RN(j/max) * 2^-shift for every sample value, and a
+    4-tap chain on the scaled samples times factor*2^shift gives the bytes of the unscaled chain."""
+    rng = np.random.default_rng(5)
+    for maxv, c1, c2, shift in ((255, 65793.0 / 2 ** 24, 2.0 ** -24, 14), (65535, 2.0 ** -16, 2.0 ** -16 + 2.0 ** -32, 6)):
+        kd = np.float32(c1 * 2.0 ** (149 - shift))
+        assert np.isfinite(kd) and float(kd) == c1 * 2.0 ** (149 - shift)
+        j = np.arange(maxv + 1, dtype=np.float64)
+        d = j * 2.0 ** -149                                                       # exact in float64
+        hi = d * float(kd)
+        assert np.all(hi == j * c1 * 2.0 ** -shift) and np.all(hi.astype(np.float32).astype(np.float64) == hi)
+        p = (hi * c2 + hi).astype(np.float32)                                     # <= 48 significant bits: exact in float64
+        ref = j.astype(np.float32) / np.float32(maxv)
+        assert np.array_equal(p.astype(np.float64) * 2.0 ** shift, ref.astype(np.float64))
+        # linearity of the chains under the power-of-two scale (float32 FMA emulated in float64: products of two float32 are
+        # exact, the sum is rounded once to float32 -- double rounding cannot occur within 53 bits here because the operands
+        # share the scale): same integer result for random 4-tap windows and the dyadic / Lanczos-like weights
+        for w in (np.array([-0.09375, 0.59375, 0.59375, -0.09375]), np.array([-0.0703125, 0.5703125, 0.5703125, -0.0703125]),
+                  np.array([-0.064453125, 0.564453125, 0.564453125, -0.064453125])):
+            jj = rng.integers(0, maxv + 1, (4000, 4))
+            ps = p[jj].astype(np.float64); pu = ref[jj].astype(np.float64)
+
+            def chain(x):
+                t = np.float32(w[1] * x[:, 1]).astype(np.float64)
+                for k in (0, 2, 3):
+                    t = np.float32(w[k] * x[:, k] + t).astype(np.float64)
+                return t
+            hs, hu = chain(ps), chain(pu)
+            assert np.array_equal(hs * 2.0 ** shift, hu)
+            os_ = np.trunc(np.float32(hs * (maxv * 2.0 ** shift)).astype(np.float64))
+            ou = np.trunc(np.float32(hu * maxv).astype(np.float64))
+            assert np.array_equal(os_, ou)
+
+
+def test_median5_stream_blocks_are_in_sync_and_exact(tmp_path):
+    """tools/gen_median5_stream.py verifies its min/max blocks (0-1 principle on sorted inputs + random bytes + the whole
+    25-sample pair construction) before writing them; the committed median5_nets.inc must be what it generates"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "median5_nets.inc"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_median5_stream.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == open(os.path.join(root, "gmat_b200", "csrc", "median5_nets.inc")).read()
+
+
 def test_bicubic_coefficients_closed_form():
     # exact 2:1: fx = 0.5 for every output; A = -0.75 gives dyadic weights, default A = 0 a 2x2 box
     co, po = orc.filter_table(orc.ALGO["bicubic"], 3840, 1920, -0.75)
