@@ -189,47 +189,94 @@ __device__ __forceinline__ void store_rgb_px(uint8_t *p, int r, int g, int b) {
 // ---------------------------------------------------------------------------
 // FMAF: which of the reference's two roundings of the chain (csc_core.cuh): libgpuscale's 8-bit kernels compile to
 // the FADD form, its 16-bit kernels and every kernel of metrans' NvCodec/ColorSpace.cu to the FMA form.
-template <int L, int SBITS, int DST, bool SPARSE, bool FMAF = (SBITS == 16)>
+// raw words of one aligned 8 x 2 tile of an 8-bit source (the vector path of load_yuv_tile, split so that the loads of several
+// tiles can be in flight while only 6 registers per tile are held)
+struct RawTile8 { uint2 y0, y1, c; };
+template <int L>
+__device__ __forceinline__ RawTile8 load_raw_tile8(const Img &s, long long fz, int x0, int y0) {
+    RawTile8 R;
+    const uint8_t *py = s.pl[0].p + fz * s.pl[0].bstride + (size_t)y0 * s.pl[0].pitch + x0;
+    R.y0 = ldg64(py); R.y1 = ldg64(py + s.pl[0].pitch);
+    if (L == L_NV12) R.c = ldg64(s.pl[1].p + fz * s.pl[1].bstride + (size_t)(y0 >> 1) * s.pl[1].pitch + x0);
+    else {
+        R.c.x = ldg32(s.pl[1].p + fz * s.pl[1].bstride + (size_t)(y0 >> 1) * s.pl[1].pitch + (x0 >> 1));
+        R.c.y = ldg32(s.pl[2].p + fz * s.pl[2].bstride + (size_t)(y0 >> 1) * s.pl[2].pitch + (x0 >> 1));
+    }
+    return R;
+}
+template <int L>
+__device__ __forceinline__ void unpack_raw_tile8(const RawTile8 &R, float (&ym)[2][8], float (&um)[4], float (&vm)[4]) {
+    ym[0][0] = byte_magic<0>(R.y0.x); ym[0][1] = byte_magic<1>(R.y0.x); ym[0][2] = byte_magic<2>(R.y0.x); ym[0][3] = byte_magic<3>(R.y0.x);
+    ym[0][4] = byte_magic<0>(R.y0.y); ym[0][5] = byte_magic<1>(R.y0.y); ym[0][6] = byte_magic<2>(R.y0.y); ym[0][7] = byte_magic<3>(R.y0.y);
+    ym[1][0] = byte_magic<0>(R.y1.x); ym[1][1] = byte_magic<1>(R.y1.x); ym[1][2] = byte_magic<2>(R.y1.x); ym[1][3] = byte_magic<3>(R.y1.x);
+    ym[1][4] = byte_magic<0>(R.y1.y); ym[1][5] = byte_magic<1>(R.y1.y); ym[1][6] = byte_magic<2>(R.y1.y); ym[1][7] = byte_magic<3>(R.y1.y);
+    if (L == L_NV12) {
+        um[0] = byte_magic<0>(R.c.x); vm[0] = byte_magic<1>(R.c.x); um[1] = byte_magic<2>(R.c.x); vm[1] = byte_magic<3>(R.c.x);
+        um[2] = byte_magic<0>(R.c.y); vm[2] = byte_magic<1>(R.c.y); um[3] = byte_magic<2>(R.c.y); vm[3] = byte_magic<3>(R.c.y);
+    } else {
+        um[0] = byte_magic<0>(R.c.x); um[1] = byte_magic<1>(R.c.x); um[2] = byte_magic<2>(R.c.x); um[3] = byte_magic<3>(R.c.x);
+        vm[0] = byte_magic<0>(R.c.y); vm[1] = byte_magic<1>(R.c.y); vm[2] = byte_magic<2>(R.c.y); vm[3] = byte_magic<3>(R.c.y);
+    }
+}
+
+// TILES: row pairs per thread.  The loads of every pair are issued before the first conversion: with one pair a thread has 24
+// bytes in flight (18 KB per SM at 24 resident warps, half of what 6.5 TB/s x the loaded DRAM latency asks for; ncu:
+// long-scoreboard 6.7 per issue, 41 % issue-active); 8-bit sources run two.
+template <int L, int SBITS, int DST, bool SPARSE, bool FMAF = (SBITS == 16), int TILES = 1>
 #ifndef GMATB_Y2R_MINB
 #define GMATB_Y2R_MINB 4
 #endif
-__global__ void __launch_bounds__(256, GMATB_Y2R_MINB) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
+__global__ void __launch_bounds__(256, TILES == 1 ? GMATB_Y2R_MINB : 3) yuv2rgb_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
-    const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
-    if (x0 >= src.w || y0 >= src.h) return;
+    const int yb = (blockIdx.y * 8 + threadIdx.y) * 2 * TILES;
+    if (x0 >= src.w || yb >= src.h) return;
     const long long fz = blockIdx.z;
-    const bool full = vec_ok && (x0 + 8 <= src.w) && (y0 + 2 <= src.h);
 
-    float ym[2][8], um[4], vm[4];
-    load_yuv_tile<L, SBITS>(src, fz, x0, y0, full, ym, um, vm);
+    static_assert(TILES == 1 || SBITS == 8, "several tiles per thread: 8-bit sources");
+    RawTile8 raw[TILES];
+    bool full[TILES];
+#pragma unroll
+    for (int t = 0; t < TILES; t++) {
+        const int y0 = yb + 2 * t;
+        full[t] = vec_ok && (x0 + 8 <= src.w) && (y0 + 2 <= src.h);
+        if (TILES > 1 && full[t]) raw[t] = load_raw_tile8<L>(src, fz, x0, y0);
+    }
 
     constexpr float YB = -(GMATB_MAGIC + (SBITS == 8 ? 16.f : 4096.f));
     constexpr float CB = -(GMATB_MAGIC + (SBITS == 8 ? 128.f : 32768.f));
-    int r[2][8], g[2][8], b[2][8];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float fu, fv;
-        upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
-        ChromaTerms t = chroma_terms<SPARSE, FMAF>(fu, fv, M);
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
-            csc_pair_i<SPARSE, FMAF>(fy2, t, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
-                                     b[rr][2 * j], b[rr][2 * j + 1]);
-        }
-    }
     constexpr int BPP = dst_bpp(DST);
-    uint8_t *pd = dst.pl[0].p + fz * dst.pl[0].bstride + (size_t)y0 * dst.pl[0].pitch + (size_t)x0 * BPP;
-    if (full) {
-        store_rgb_row8<DST, SBITS>(pd, r[0], g[0], b[0]);
-        store_rgb_row8<DST, SBITS>(pd + dst.pl[0].pitch, r[1], g[1], b[1]);
-    } else {
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++)
+    for (int t = 0; t < TILES; t++) {
+        const int y0 = yb + 2 * t;
+        if (y0 >= src.h) break;
+        float ym[2][8], um[4], vm[4];
+        if (TILES > 1 && full[t]) unpack_raw_tile8<L>(raw[t], ym, um, vm);
+        else load_yuv_tile<L, SBITS>(src, fz, x0, y0, full[t], ym, um, vm);
+        int r[2][8], g[2][8], b[2][8];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (x0 + i < src.w && y0 + rr < src.h)
-                    store_rgb_px<DST, SBITS>(pd + (size_t)rr * dst.pl[0].pitch + i * BPP, r[rr][i], g[rr][i], b[rr][i]);
+        for (int j = 0; j < 4; j++) {
+            float fu, fv;
+            upk(add2(pk(um[j], vm[j]), bc(CB)), fu, fv);
+            ChromaTerms ct = chroma_terms<SPARSE, FMAF>(fu, fv, M);
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                f2 fy2 = add2(pk(ym[rr][2 * j], ym[rr][2 * j + 1]), bc(YB));
+                csc_pair_i<SPARSE, FMAF>(fy2, ct, M, r[rr][2 * j], r[rr][2 * j + 1], g[rr][2 * j], g[rr][2 * j + 1],
+                                         b[rr][2 * j], b[rr][2 * j + 1]);
+            }
+        }
+        uint8_t *pd = dst.pl[0].p + fz * dst.pl[0].bstride + (size_t)y0 * dst.pl[0].pitch + (size_t)x0 * BPP;
+        if (full[t]) {
+            store_rgb_row8<DST, SBITS>(pd, r[0], g[0], b[0]);
+            store_rgb_row8<DST, SBITS>(pd + dst.pl[0].pitch, r[1], g[1], b[1]);
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (x0 + i < src.w && y0 + rr < src.h)
+                        store_rgb_px<DST, SBITS>(pd + (size_t)rr * dst.pl[0].pitch + i * BPP, r[rr][i], g[rr][i], b[rr][i]);
+        }
     }
 }
 
@@ -439,10 +486,9 @@ __host__ __device__ constexpr bool srgb_is16(int s) { return s >= S_RGBA64; }
 // RZ(q + 2^23)), truncation is the round-toward-zero multiply by 2^-149 and the clamp is the saturating I2IP
 // pack.  (The I2F form ran at 55 % of the HBM roofline, conversion-unit bound.)
 template <int SRC, int L>
-__device__ __forceinline__ void rgb2yuv_tile8(const Img &src, const Img &dst, const Mat9 &M, long long fz, int x0, int y0) {
+__device__ __forceinline__ void rgb2yuv_tile8_load(const Img &src, long long fz, int x0, int y0, uint32_t (&w)[2][2 * srgb_bpp(SRC)]) {
     constexpr int BPP = srgb_bpp(SRC);
     constexpr int NW = 2 * BPP;                       // 32-bit words per 8-pixel row
-    uint32_t w[2][NW];
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const uint8_t *row = src.pl[0].p + fz * src.pl[0].bstride + (size_t)(y0 + rr) * src.pl[0].pitch + (size_t)x0 * BPP;
@@ -455,6 +501,11 @@ __device__ __forceinline__ void rgb2yuv_tile8(const Img &src, const Img &dst, co
             w[rr][0] = a.x; w[rr][1] = a.y; w[rr][2] = b.x; w[rr][3] = b.y; w[rr][4] = c.x; w[rr][5] = c.y;
         }
     }
+}
+template <int SRC, int L>
+__device__ __forceinline__ void rgb2yuv_tile8_convert(const uint32_t (&w)[2][2 * srgb_bpp(SRC)], const Img &dst, const Mat9 &M,
+                                                      long long fz, int x0, int y0) {
+    constexpr int BPP = srgb_bpp(SRC);
     const f2 nm = bc(-GMATB_MAGIC), z = bc(GMATB_TWO_M149);
     f2 c2[3][8];                                      // [component r,g,b][column] = (top, bottom), exact integers as floats
 #pragma unroll
@@ -510,12 +561,8 @@ template <int SRC, int L, int DBITS>
 #ifndef GMATB_R2Y_MINB
 #define GMATB_R2Y_MINB 3
 #endif
-__global__ void __launch_bounds__(256, GMATB_R2Y_MINB) rgb2yuv_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
-    const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
+__device__ __forceinline__ void rgb2yuv_tile(const Img &src, const Img &dst, const Mat9 &M, int vec_ok, long long fz, int x0, int y0) {
     const int W = src.w, H = src.h;
-    if (x0 >= W || y0 >= H) return;
-    const long long fz = blockIdx.z;
     constexpr int BPP = srgb_bpp(SRC);
     constexpr float LOW = DBITS == 8 ? 16.f : 4096.f, MID = DBITS == 8 ? 128.f : 32768.f;
     constexpr int DMAX = DBITS == 8 ? 255 : 65535;
@@ -524,7 +571,12 @@ __global__ void __launch_bounds__(256, GMATB_R2Y_MINB) rgb2yuv_kernel(Img src, I
 
     const bool full = vec_ok && x0 + 8 <= W && y0 + 2 <= H;
     if constexpr (!srgb_is16(SRC) && DBITS == 8) {
-        if (full) { rgb2yuv_tile8<SRC, L>(src, dst, M, fz, x0, y0); return; }
+        if (full) {
+            uint32_t w[2][2 * BPP];
+            rgb2yuv_tile8_load<SRC, L>(src, fz, x0, y0, w);
+            rgb2yuv_tile8_convert<SRC, L>(w, dst, M, fz, x0, y0);
+            return;
+        }
     }
     int cr[2][8], cg[2][8], cb[2][8];
     if (full) {
@@ -637,6 +689,37 @@ __global__ void __launch_bounds__(256, GMATB_R2Y_MINB) rgb2yuv_kernel(Img src, I
             uint8_t *qv = dst.pl[2].p + fz * dst.pl[2].bstride + (size_t)cy * dst.pl[2].pitch + (size_t)cx * DBS;
             if (DBITS == 8) { *qu = u; *qv = v; }
             else { *reinterpret_cast<uint16_t *>(qu) = u; *reinterpret_cast<uint16_t *>(qv) = v; }
+        }
+    }
+}
+
+// 8-bit rgb -> 8-bit yuv runs two row pairs per thread with the loads of both issued first (96 bytes in flight per thread: the
+// one-pair form measured 74 % of the HBM roofline, latency-bound); every other instantiation one pair.
+template <int SRC, int DBITS> __host__ __device__ constexpr int r2y_tiles() { return (!srgb_is16(SRC) && DBITS == 8) ? 2 : 1; }
+template <int SRC, int L, int DBITS>
+__global__ void __launch_bounds__(256, (r2y_tiles<SRC, DBITS>() > 1 ? 2 : GMATB_R2Y_MINB)) rgb2yuv_kernel(Img src, Img dst, Mat9 M, int vec_ok) {
+    constexpr int T = r2y_tiles<SRC, DBITS>();
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    const int yb = (blockIdx.y * 8 + threadIdx.y) * 2 * T;
+    if (x0 >= src.w || yb >= src.h) return;
+    const long long fz = blockIdx.z;
+    if constexpr (T == 1) {
+        rgb2yuv_tile<SRC, L, DBITS>(src, dst, M, vec_ok, fz, x0, yb);
+    } else {
+        uint32_t w[T][2][2 * srgb_bpp(SRC)];
+        bool full[T];
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const int y0 = yb + 2 * t;
+            full[t] = vec_ok && x0 + 8 <= src.w && y0 + 2 <= src.h;
+            if (full[t]) rgb2yuv_tile8_load<SRC, L>(src, fz, x0, y0, w[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const int y0 = yb + 2 * t;
+            if (y0 >= src.h) break;
+            if (full[t]) rgb2yuv_tile8_convert<SRC, L>(w[t], dst, M, fz, x0, y0);
+            else rgb2yuv_tile<SRC, L, DBITS>(src, dst, M, 0, fz, x0, y0);
         }
     }
 }
@@ -814,11 +897,12 @@ static int dst_code(int fmt) {
     }
 }
 
+#define Y2R_TILES(SBITS) ((SBITS) == 8 ? 2 : 1)
 template <int L, int SBITS, bool SPARSE>
 static int launch_yuv2rgb_dst(int dc, dim3 g, cudaStream_t st, const Img &s, const Img &d, const Mat9 &M, int vec) {
     dim3 b(32, 8);
     switch (dc) {
-#define C(D) case D: yuv2rgb_kernel<L, SBITS, D, SPARSE><<<g, b, 0, st>>>(s, d, M, vec); break;
+#define C(D) case D: yuv2rgb_kernel<L, SBITS, D, SPARSE, (SBITS == 16), Y2R_TILES(SBITS)><<<g, b, 0, st>>>(s, d, M, vec); break;
         C(D_RGB24) C(D_BGR24) C(D_RGBA) C(D_BGRA) C(D_RGB48) C(D_BGR48) C(D_RGBA64) C(D_BGRA64)
 #undef C
     default: return GMATB_ERR_UNSUPPORTED;
@@ -881,8 +965,8 @@ int yuv2rgb_launch(const GmatbImage *src, const GmatbImage *dst, const Mat9 &M, 
     if (!to_img(src, &s, fmt_planes(src->format)) || !to_img(dst, &d, 1)) return GMATB_ERR_INVAL;
     const bool sparse = (M.m[1] == 0.f && M.m[8] == 0.f);
     const int vec = aligned16(s, fmt_planes(src->format)) && aligned16(d, 1);
-    dim3 g = tile_grid(s.w, s.h, 2, src->batch);
-#define GO(L, B) (sparse ? launch_yuv2rgb_dst<L, B, true>(dc, g, st, s, d, M, vec) : launch_yuv2rgb_dst<L, B, false>(dc, g, st, s, d, M, vec))
+#define GO(L, B) (sparse ? launch_yuv2rgb_dst<L, B, true>(dc, tile_grid(s.w, s.h, 2 * Y2R_TILES(B), src->batch), st, s, d, M, vec) \
+                        : launch_yuv2rgb_dst<L, B, false>(dc, tile_grid(s.w, s.h, 2 * Y2R_TILES(B), src->batch), st, s, d, M, vec))
     switch (src->format) {
     case GMATB_FMT_NV12:    return GO(L_NV12, 8);
     case GMATB_FMT_YUV420P: return GO(L_I420, 8);
@@ -921,9 +1005,10 @@ static int launch_rgb2yuv_src(int dfmt, dim3 g, cudaStream_t st, const Img &s, c
     dim3 b(32, 8);
     const int np = (dfmt == GMATB_FMT_YUV420P) ? 3 : 2;
     const int vec = aligned16(s, 1) && aligned16(d, np);
+    const dim3 g8 = tile_grid(s.w, s.h, 2 * r2y_tiles<SRC, 8>(), (int)g.z);
     switch (dfmt) {
-    case GMATB_FMT_NV12:    rgb2yuv_kernel<SRC, L_NV12, 8><<<g, b, 0, st>>>(s, d, M, vec); break;
-    case GMATB_FMT_YUV420P: rgb2yuv_kernel<SRC, L_I420, 8><<<g, b, 0, st>>>(s, d, M, vec); break;
+    case GMATB_FMT_NV12:    rgb2yuv_kernel<SRC, L_NV12, 8><<<g8, b, 0, st>>>(s, d, M, vec); break;
+    case GMATB_FMT_YUV420P: rgb2yuv_kernel<SRC, L_I420, 8><<<g8, b, 0, st>>>(s, d, M, vec); break;
     case GMATB_FMT_P010LE:
     case GMATB_FMT_P016LE:
         if (!srgb_is16(SRC)) return GMATB_ERR_UNSUPPORTED;
