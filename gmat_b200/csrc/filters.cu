@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(256) crop_kernel(PImg s, PImg d, int cx, int c
     uint8_t *pd = d.p + fz * d.bstride + (size_t)y * d.pitch + b0;
     if (dst_vec && b0 + 16 <= rowb) {
         const uintptr_t a = (uintptr_t)ps;
+        // a 16-byte aligned window origin (e.g. the centred 1080p window of a 4K rgb24 frame: 2880 bytes into the row) is a plain
+        // 128-bit copy; the branch is uniform over the launch
+        if ((a & 15) == 0) { stg128(pd, ldg128(ps)); return; }
         const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         const unsigned sh = (unsigned)(a & 3) * 8;
         uint32_t w0 = __ldcs(q), w1 = __ldcs(q + 1), w2 = __ldcs(q + 2), w3 = __ldcs(q + 3);

@@ -27,3 +27,9 @@ report("NV12 -> RGB24", timeit(lambda: g.yuv2rgb(src, full)), B * (12441600 + 24
 report("YUV420P -> RGB24", timeit(lambda: g.yuv2rgb(i420, full)), B * (12441600 + 24883200))
 report("NV12 -> RGBA", timeit(lambda: g.yuv2rgb(src, fa)), B * (12441600 + 33177600))
 report("RGB24 -> NV12", timeit(lambda: g.rgb2yuv(full, back)), B * (12441600 + 24883200))
+a = FrameBatch(FMT.RGB24, 3840, 2160, 32, device=dev); a.buf.random_(0, 256)
+cr = FrameBatch(FMT.RGB24, 1920, 1080, 32, device=dev)
+ms = timeit(lambda: g.crop(a, cr, -1, -1))
+print(f"crop 4K -> 1080p centre rgb24        {ms:7.3f} ms {32*2*6220800/ms/1e6:7.0f} GB/s {32*2*6220800/ms/1e6/PEAK*100:6.1f}%", flush=True)
+ms = timeit(lambda: g.crop(a, cr, 961, 3))
+print(f"crop 4K -> 1080p at (961, 3) rgb24   {ms:7.3f} ms {32*2*6220800/ms/1e6:7.0f} GB/s {32*2*6220800/ms/1e6/PEAK*100:6.1f}%", flush=True)
