@@ -46,7 +46,7 @@ def smooth(w, h, c):
 
 @pytest.mark.parametrize("c", [3, 4])
 @pytest.mark.parametrize("k", [3, 5])
-@pytest.mark.parametrize("w,h", [(640, 360), (1920, 1080), (131, 77)])
+@pytest.mark.parametrize("w,h", [(640, 360), (1920, 1080), (131, 77), (3840, 2160), (36, 21)])
 def test_median_equals_cv2_medianBlur(dev, c, k, w, h):
     """cv2.medianBlur: exact k x k median, BORDER_REPLICATE -- the same definition: every byte equal"""
     img = noise(w, h, c, 3 + k)
