@@ -246,9 +246,13 @@ static NormK norm_k(int bits) {
 // 16 -> 128 registers, the v3 kernel needs ~120 to keep every constant and both row-pair buffers
 // resident (at 96 it spills and rematerialises parameters inside the loop).  The 2-tap instantiation fits 80
 // registers, but 16 / 20 / 24 resident warps all measure 1.50-1.54 Tpx/s: it is fma-pipe bound, not latency bound.
+// Re-measured on the all-packed kernel (round 2, 64 4K frames): MINB 12 (168 registers) 1010, 16 (128) 1023, 20 (96, spills) 986 Gpx/s.
+#ifndef GMATB_FUSED3_MINB
+#define GMATB_FUSED3_MINB 16
+#endif
 template <int L, int SBITS, int DST>
 static void launch_fused_t(bool taps2, bool wrap, dim3 g, cudaStream_t st, const Fused3Params &P) {
-#define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, 16><<<g, 32, 0, st>>>(P)
+#define K(T, W) fused_csc_scale2_v3_kernel<L, SBITS, DST, T, W, GMATB_FUSED3_MINB><<<g, 32, 0, st>>>(P)
     if (wrap) { if (taps2) K(true, true); else K(false, true); }
     else      { if (taps2) K(true, false); else K(false, false); }
 #undef K
