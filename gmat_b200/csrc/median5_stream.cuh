@@ -60,7 +60,8 @@ __device__ __forceinline__ void med5_phase(unsigned (&sc)[NOUT + 4][5], bool led
 }
 
 template <int BPP, int NOUT>
-__global__ void __launch_bounds__(128, 2) median5_stream_kernel(const Med3Params P) {
+// resident CTAs per SM: 3-byte pixels 3 (168 registers, 64 bytes of spills: 130 -> 134 Gpx/s), 4-byte pixels 2 (3 measured 88 -> 80)
+__global__ void __launch_bounds__(128, BPP == 3 ? 3 : 2) median5_stream_kernel(const Med3Params P) {
     static_assert(NOUT % 2 == 0 && (NOUT * BPP) % 4 == 0, "pairs of outputs, whole words");
     constexpr int S = NOUT * BPP;                      // output byte columns per thread
     constexpr int HB = 2 * BPP;                        // halo bytes per side
